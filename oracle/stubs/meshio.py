@@ -1,0 +1,6 @@
+"""Stand-in for meshio (absent from this image); oracle test infrastructure only.
+Any use raises: the hot path never touches it."""
+
+
+def __getattr__(name):
+    raise ImportError("meshio is not available in this image (oracle stub): " + name)
