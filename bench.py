@@ -1,0 +1,315 @@
+"""Headline benchmark: SIMP_COMP iterations/s on the ~4 M DOF Q4 plane-stress cantilever (BASELINE.json
+configs[1] mesh, 2000 x 1000), plus the roofline of the dominant kernel and a CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl femol|reference] [--nx 2000 --ny 1000]
+
+A "step" is one SIMP_COMP iteration (TOM_SIMP.py:48-60): assemble K(x^p) -> PCG solve -> compliance
+sensitivities -> filter -> OC update.  Steps continue one optimisation trajectory (densities evolve; the PCG
+is warm-started from the previous displacement, as any SIMP driver would).
+
+  value  device-resident throughput: densities stay in HBM between steps; timed with CUDA events.
+  e2e    the same step through the public API with HOST buffers: pinned-host densities copied in, new
+         densities + (change, objective) copied out, every step, inside the timed region.
+  N > 1  independent designs sharded one per GPU (north-star "design batches"): no data-path collective,
+         weak scaling; time = max over ranks.
+  --impl reference   the CPU oracle port (vectorised numpy/scipy restatement of the reference algorithm; the
+         reference itself is pure Python and cannot travel to the GPU box) on a bounded sample mesh.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'simp_iterations_per_s'
+UNIT = 'SIMP iterations/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='femol', choices=['femol', 'reference'])
+    ap.add_argument('--nx', type=int, default=2000)
+    ap.add_argument('--ny', type=int, default=1000)
+    ap.add_argument('--rtol', type=float, default=1e-8)
+    ap.add_argument('--precond', default='block_jacobi')
+    ap.add_argument('--sample-nx', type=int, default=400, help='CPU baseline sample mesh')
+    ap.add_argument('--sample-ny', type=int, default=200)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def workload_name(nx, ny):
+    return 'Q4 plane-stress cantilever SIMP_COMP, %dx%d structured mesh (%.2fM DOF), volfrac 0.4, p=3, rmin 1.5' % (
+        nx, ny, 2 * (nx + 1) * (ny + 1) / 1e6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU oracle leg (cpu_baseline and --impl reference)
+# ---------------------------------------------------------------------------------------------------------------
+def oracle_problem(nx, ny):
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import femol_oracle as o
+    Lx, Ly = float(nx), float(ny)
+    pts, cells = o.rectangle_points_quads(Lx, Ly, nx, ny)
+    fixed = [(o.inside_box([0], [[0, Ly]]), [0, 1])]
+    forces = [([0, -1.0], o.inside_box([Lx], [[Ly / 2 - 1, Ly / 2 + 1]]))]
+    return o.CompProblem('Q4', pts, cells, 2, o.iso_tensors(1, 0.3, 1), fixed, forces, structured=True,
+                         volfrac=0.4, penal=3, rmin=1.5)
+
+
+def cpu_sample(nx, ny, full_elems, steps=1, warmup=0):
+    """Times `steps` oracle SIMP iterations on an nx x ny sample and scales linearly in the element count
+    (favourable to the CPU: its sparse direct solve grows faster than linearly)."""
+    P = oracle_problem(nx, ny)
+    for _ in range(warmup):
+        P.iterate()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        P.iterate()
+    dt = (time.perf_counter() - t0) / steps
+    scale = full_elems / float(nx * ny)
+    return dt, 1.0 / (dt * scale)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    full = args.nx * args.ny
+    t_all = time.perf_counter()
+    P = oracle_problem(args.sample_nx, args.sample_ny)
+    for _ in range(args.warmup):
+        P.iterate()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        P.iterate()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = 1.0 / (dt * full / float(args.sample_nx * args.sample_ny))
+    sample = ('%dx%d mesh (%.3f of the %dx%d elements) per step, seconds scaled linearly in elements'
+              % (args.sample_nx, args.sample_ny, args.sample_nx * args.sample_ny / float(full), args.nx, args.ny))
+    cores = 1
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3 * full / float(args.sample_nx * args.sample_ny),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': workload_name(args.nx, args.ny)},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0, 'wall_s': time.perf_counter() - t_all}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU leg
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith('active')})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def build_gpu_problem(F, nx, ny, rtol, precond):
+    Lx, Ly = float(nx), float(ny)
+    mesh = F.mesh.rectangle_Q4(Lx, Ly, nx, ny)
+    problem = F.FEM_Problem('displacement', 'plane', mesh)
+    problem.define_materials(F.materials.general_isotropic())
+    problem.define_tensors(1)
+    problem.add_fixed_domain(F.domains.inside_box([0], [[0, Ly]]), ddls=[0, 1])
+    problem.add_forces([0, -1.0], F.domains.inside_box([Lx], [[Ly / 2 - 1, Ly / 2 + 1]]))
+    problem.solver_rtol = rtol
+    problem.preconditioner = precond
+    opt = F.SIMP_COMP(problem, volfrac=0.4, penal=3, rmin=1.5)
+    opt.archive = False
+    return problem, opt
+
+
+def time_kernel(torch, fn, reps):
+    """Average device time of `fn` (one kernel launch) with CUDA events on the current stream."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e-3 / reps
+
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import femol_b200 as F
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    L = F._lib.require_gpu()
+    t_setup = time.perf_counter()
+    problem, opt = build_gpu_problem(F, args.nx, args.ny, args.rtol, args.precond)
+    d = problem.device
+    n_elem = d.n_elem
+    setup_s = time.perf_counter() - t_setup
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps -------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        opt.iterate()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    L.femol_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pcg_iters, log = [], []
+    ev0.record()
+    for _ in range(args.steps):
+        opt.iterate()
+        pcg_iters.append(problem.solver_info['iterations'])
+        log.append((opt.change, opt.c, problem.solver_info['relres']))
+    ev1.record()
+    barrier()
+    launches = int(L.femol_launch_count(0))
+    dt = ev0.elapsed_time(ev1) * 1e-3
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end steps with host buffers ---------------------------------------------------------------
+    x_host = torch.empty(n_elem, dtype=torch.float64).pin_memory()
+    x_host.copy_(opt.x_device)
+    out_host = torch.empty(n_elem, dtype=torch.float64).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        opt.x_device.copy_(x_host, non_blocking=True)        # H2D: this step's input densities
+        opt.iterate()                                         # includes the (change, objective) read-back
+        out_host.copy_(opt.x_device, non_blocking=True)       # D2H: this step's result
+        torch.cuda.current_stream().synchronize()
+        x_host, out_host = out_host, x_host
+    e1.record()
+    barrier()
+    dt_e2e = e0.elapsed_time(e1) * 1e-3
+
+    if world > 1:
+        t = torch.tensor([dt, dt_e2e], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, dt_e2e = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel (SpMV inside PCG) and of the assembly ----------------------------
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
+        n, nnz, nnzn = d.n, d.nnz, d.nnz_node
+        xv = torch.randn(n, dtype=torch.float64, device='cuda')
+        yv = torch.empty_like(xv)
+        kv = problem.K_values
+        st = F._lib.stream()
+        t_spmv = time_kernel(torch, lambda: L.femol_spmv(d.plan, kv.data_ptr(), xv.data_ptr(), yv.data_ptr(), st), 20)
+        spmv_bytes = 8 * nnz + 4 * nnzn + 4 * (d.n_nodes + 1) + 16 * n
+        Eb, pe = problem._element_matrices('K', False)
+        vals = torch.empty(nnz, dtype=torch.float64, device='cuda')
+        mask = problem._fixed_mask()
+        xp = d.xpow
+        # assembly kernel alone (x^p already in the workspace): pass x = NULL is "no scaling", so time the full call
+        t_asm = time_kernel(torch, lambda: L.femol_assemble(d.plan, Eb.data_ptr(), pe, None, 0, opt.x_device.data_ptr(), 3.0,
+                                                            mask.data_ptr(), xp.data_ptr(), vals.data_ptr(), st), 10)
+        asm_bytes = 8 * nnz + 4 * (nnzn + 1) + 4 * n_elem * d.nn * d.nn + 4 * nnzn + 8 * n_elem * 3
+        total_pcg = int(np.sum(pcg_iters))
+        roofline = {'kernel': 'spmv_node_kernel<2,4> (q = K p inside femol_pcg)', 'bound': 'hbm',
+                    'achieved': spmv_bytes / t_spmv / 1e9, 'peak': peak, 'unit': 'GB/s',
+                    'frac': spmv_bytes / t_spmv / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': spmv_bytes, 'avg_launch_s': t_spmv,
+                    'launches_in_timed_region': total_pcg,
+                    'share_of_step': total_pcg * t_spmv / dt if dt > 0 else None}
+        roofline_asm = {'kernel': 'assemble_kernel<2,4> + density_power', 'bound': 'hbm',
+                        'achieved': asm_bytes / t_asm / 1e9, 'peak': peak, 'unit': 'GB/s',
+                        'frac': asm_bytes / t_asm / 1e9 / peak, 'traffic': None,
+                        'algorithmic_bytes_per_launch': asm_bytes, 'avg_launch_s': t_asm}
+        cpu = None
+        if not args.no_cpu_baseline:
+            cdt, cval = cpu_sample(args.sample_nx, args.sample_ny, args.nx * args.ny, steps=1, warmup=0)
+            cpu = {'value': cval, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                   'sample': '1 SIMP iteration of the numpy/scipy oracle on a %dx%d mesh (%.1f s), scaled linearly to %dx%d elements'
+                             % (args.sample_nx, args.sample_ny, cdt, args.nx, args.ny)}
+        value = world * args.steps / dt
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': workload_name(args.nx, args.ny), 'ndof': n, 'nnz': nnz,
+                           'pcg': {'precond': args.precond, 'rtol': args.rtol, 'iterations_per_step': pcg_iters,
+                                   'warm_start': True},
+                           'l2_policy': 'inputs larger than L2 (CSR values %.0f MB per SpMV >> 126 MB L2)' % (8 * nnz / 1e6),
+                           'parallelism': 'one independent design per GPU' if world > 1 else 'single GPU',
+                           'setup_s': setup_s},
+                'e2e': {'value': world * args.steps / dt_e2e, 'unit': UNIT, 'h2d_bytes_per_step': 8 * n_elem,
+                        'd2h_bytes_per_step': 8 * n_elem + 64},
+                'gpu_launches': launches, 'roofline': roofline, 'roofline_assembly': roofline_asm,
+                'cpu_baseline': cpu, 'clocks': clocks,
+                'trajectory': {'change': [l[0] for l in log], 'compliance': [l[1] for l in log],
+                               'pcg_relres': [l[2] for l in log]}}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,377 @@
+"""FEM_Problem — B200-native mirror of the reference's FEMOL/FEM.py.
+
+Same public surface (`FEM_Problem(physics, model, mesh)`, `define_materials`, `define_tensors`,
+`add_fixed_domain`, `add_forces`, `assemble(which, X, p, q)`, `solve(...)`, attributes `K`, `M`, `F`,
+`tensors`, `coat_tensors`, `ho`, `coating`, `N_dof`) and the same conventions, but the per-iteration work
+runs in hand-written sm_100a kernels behind the C-ABI of include/femol_b200.h:
+
+  reference (FEM.py)                                   here
+  _K/_M_*_mesh_data_* :550-871 + BC scan :902-930     femol_ke_batch / femol_me_batch + femol_assemble
+  csr_matrix + sum_duplicates :498-501                 symbolic plan (femol_plan_create) + femol_assemble
+  spsolve :258-265                                     femol_pcg (Jacobi / block-Jacobi PCG, warm start)
+  dense eigh :267-295 / eigsh :234                     LOBPCG over femol_spmm / femol_gram / ... (lobpcg.py)
+
+K / M live on the device as CSR values in the plan's order; `problem.K` / `problem.M` materialise scipy CSR
+matrices on demand (bit-identical pattern: sorted int32 indices, explicit zeros kept).  There is no CPU
+fallback: without the CUDA library or a GPU every compute call raises.
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse
+import torch
+
+from . import _lib
+from . import elements
+from . import lobpcg as _lobpcg
+from .laminate import Layup
+from .mesh import Mesh
+
+__all__ = ['FEM_Problem', 'Mesh', 'Layup']
+
+_PRECOND = {'none': _lib.PRECOND_NONE, 'jacobi': _lib.PRECOND_JACOBI, 'block_jacobi': _lib.PRECOND_BLOCK_JACOBI}
+
+
+class _Device(object):
+    """Device-resident mesh data, the symbolic plan and workspaces of one FEM_Problem."""
+
+    def __init__(self, mesh, N_dof):
+        _lib.require_gpu()
+        if len(mesh.contains) != 1:
+            raise NotImplementedError('femol_b200 handles meshes with a single cell type '
+                                      '(mixed triangle/quad meshes are outside the accelerated path)')
+        self.ctype = mesh.contains[0]
+        cls = mesh.ElementClasses[self.ctype]
+        self.etype = cls.ETYPE
+        self.nn = cls.N_nodes
+        self.ndof = N_dof
+        self.dev = torch.device('cuda', torch.cuda.current_device())
+        self.n_nodes = mesh.points.shape[0]
+        self.n_elem = mesh.cells[self.ctype].shape[0]
+        self.n = self.n_nodes * N_dof
+        self.xy = torch.from_numpy(np.ascontiguousarray(mesh.points[:, :2], dtype=np.float64)).to(self.dev)
+        self.conn = torch.from_numpy(np.ascontiguousarray(mesh.cells[self.ctype], dtype=np.int32)).to(self.dev)
+        handle = ctypes.c_void_p()
+        _lib.call('femol_plan_create', self.n_elem, self.nn, N_dof, self.n_nodes, _lib.ptr(self.conn), _lib.stream(),
+                  ctypes.byref(handle))
+        self.plan = handle
+        info = (ctypes.c_int64 * 8)()
+        _lib.call('femol_plan_info', self.plan, info)
+        self.nnz_node, self.nnz = int(info[0]), int(info[1])
+        self.max_valence, self.max_row_nodes = int(info[2]), int(info[3])
+        self.xpow = torch.empty(self.n_elem, dtype=torch.float64, device=self.dev)
+        self.red_ws = torch.zeros(int(_lib.load().femol_reduce_workspace_doubles()), dtype=torch.float64, device=self.dev)
+        self._csr = None
+        self._pcg_ws = None
+
+    def __del__(self):
+        try:
+            if getattr(self, 'plan', None):
+                _lib.load().femol_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+    def csr_pattern(self):
+        if self._csr is None:
+            indptr = torch.empty(self.n + 1, dtype=torch.int32, device=self.dev)
+            indices = torch.empty(self.nnz, dtype=torch.int32, device=self.dev)
+            _lib.call('femol_plan_export_csr', self.plan, _lib.ptr(indptr), _lib.ptr(indices), _lib.stream())
+            self._csr = (indptr, indices)
+        return self._csr
+
+    def scatter_map(self):
+        out = torch.empty((self.n_elem, self.nn, self.nn), dtype=torch.int32, device=self.dev)
+        _lib.call('femol_plan_export_scatter_map', self.plan, _lib.ptr(out), _lib.stream())
+        return out
+
+    def pcg_ws(self):
+        if self._pcg_ws is None:
+            nd = int(_lib.load().femol_pcg_workspace_doubles(self.plan))
+            self._pcg_ws = torch.empty(nd, dtype=torch.float64, device=self.dev)
+        return self._pcg_ws
+
+    def to_scipy(self, vals):
+        indptr, indices = self.csr_pattern()
+        return scipy.sparse.csr_matrix((vals.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()),
+                                       shape=(self.n, self.n))
+
+
+class FEM_Problem(object):
+    """General structural FEM problem: displacement (K U = F) or modal (K v = lambda M v), plane stress
+    (2 dof / node) or Reissner-Mindlin plate (6 dof / node).  Reference: FEM.py:21-59."""
+    dof_dict = {'plane': 2, 'plate': 6}
+
+    def __init__(self, physics, model, mesh):
+        self.mesh = mesh
+        self.physics = physics
+        self.model = model
+        self.N_dof = self.dof_dict[model]
+        self.coating = False
+        # reference FEM.py:49 builds the COO index arrays here; the device plan replaces them and
+        # mesh.rows / mesh.cols stay available lazily (mesh.global_matrix_indexes)
+        ctype = mesh.contains[0]
+        if mesh.structured:
+            mesh.element = mesh.ElementClasses[ctype](mesh.points[mesh.cells[ctype][0]], N_dof=self.N_dof)
+        self.fixed_nodes = np.array([])
+        self.fixed_domains = []
+        self.fixed_ddls = []
+        self.forces = []
+        self.force_domains = []
+        self.layups = []
+        self.F = np.zeros(self.N_dof * self.mesh.N_nodes)
+        self.V = None
+        # solver controls (no reference counterpart: spsolve is direct)
+        self.solver_rtol = 1e-10
+        self.solver_max_iter = 200000
+        self.preconditioner = 'block_jacobi'
+        self.warm_start = True
+        self.n_modes = 10
+        self.modal_tol = 1e-8
+        self.modal_max_iter = 2000
+        self.solver_info = {}
+        self._dev = None
+        self._E = {}          # cached element matrices on the device
+        self._Kv = self._Mv = None
+        self._K_host = self._M_host = None
+        self._U_dev = None
+        self._X_modal = None  # last eigenvector block (warm start)
+        self._mask_key = None
+        self._mask_dev = None
+
+    # ---- set-up (host) ----------------------------------------------------------------------------
+    def define_materials(self, *materials):
+        """FEM.py:105-111"""
+        self.materials = materials
+        if len(materials) == 2:
+            self.coating = True
+        self._E.clear()
+
+    def define_tensors(self, *tensors):
+        """FEM.py:113-154: thickness (isotropic) or Layup (orthotropic), base [+ coating]."""
+        C_A, C_B, C_D, C_G, ho = [], [], [], [], []
+        for tensor, material in zip(tensors, self.materials):
+            if material.kind == 'orthotropic':
+                layup = tensor
+                ho.append(layup.hA)
+                C_A.append(layup.get_A_FEM()); C_B.append(layup.B_mat)
+                C_D.append(layup.D_mat); C_G.append(layup.G_mat)
+                self.layups.append(layup)
+            elif material.kind == 'isotropic':
+                t = tensor
+                ho.append(t)
+                C_A.append(material.plane_tensor(t)); C_B.append(material.coupled_tensor())
+                C_D.append(material.bending_tensor(t)); C_G.append(material.shear_tensor(t))
+        self.tensors = [C_A[0], C_D[0], C_G[0], C_B[0]]
+        self.ho = ho[0]
+        if len(C_A) == 2:
+            self.coat_tensors = [C_A[1], C_D[1], C_G[1], C_B[1]]
+            self.coat_ho = ho[1]
+            self.coating = True
+        self._E.clear()
+
+    def add_fixed_domain(self, domain, ddls=None):
+        """FEM.py:424-438"""
+        if ddls is None:
+            ddls = np.arange(self.N_dof)
+        self.fixed_domains.append(domain)
+        self.fixed_ddls.append(ddls)
+
+    def add_forces(self, force, domain):
+        """FEM.py:440-464: the force vector is split equally over the nodes of the domain."""
+        F = np.zeros(self.N_dof * self.mesh.N_nodes)
+        self.forces.append(force)
+        self.force_domains.append(domain)
+        nodes = self.mesh.domain_nodes(domain)
+        if len(nodes) > 0:
+            f = np.array(force, dtype=float) / len(nodes)
+            for ddl in range(self.N_dof):
+                F[self.N_dof * nodes + ddl] = f[ddl]
+        else:
+            print('invalid force domain')
+        self.F = self.F + F
+
+    # ---- device plumbing --------------------------------------------------------------------------
+    @property
+    def device(self):
+        if self._dev is None:
+            self._dev = _Device(self.mesh, self.N_dof)
+        return self._dev
+
+    def fixed_dofs(self):
+        """Sorted unique global dof numbers fixed by the registered domains."""
+        out = []
+        for domain, ddls in zip(self.fixed_domains, self.fixed_ddls):
+            nodes = self.mesh.domain_nodes(domain)
+            out.append((nodes[:, None] * self.N_dof + np.asarray(ddls)[None]).reshape(-1))
+        return np.unique(np.concatenate(out)) if out else np.zeros(0, dtype=np.int64)
+
+    def _fixed_mask(self):
+        """uint8 per node, bit d = dof d fixed (device), or None."""
+        key = (len(self.fixed_domains), tuple(tuple(np.asarray(d).tolist()) for d in self.fixed_ddls))
+        if key != self._mask_key:
+            mask = np.zeros(self.mesh.N_nodes, dtype=np.uint8)
+            nodes_all = []
+            for domain, ddls in zip(self.fixed_domains, self.fixed_ddls):
+                nodes = self.mesh.domain_nodes(domain)
+                nodes_all.append(nodes)
+                bits = np.uint8(sum(1 << int(d) for d in ddls))
+                mask[nodes] |= bits
+            self.fixed_nodes = np.concatenate(nodes_all) if nodes_all else np.array([])
+            self._mask_dev = torch.from_numpy(mask).to(self.device.dev) if self.fixed_ddls else None
+            self._mask_key = key
+        return self._mask_dev
+
+    def _x_device(self, X):
+        if X is None:
+            return None
+        if isinstance(X, dict):
+            X = X[self.mesh.contains[0]]
+        if isinstance(X, torch.Tensor):
+            return X.to(self.device.dev, torch.float64).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(self.device.dev)
+
+    def _element_matrices(self, which, coat):
+        """Cached device element matrices: (tensor [1 or n_elem, s, s], per_elem flag).
+        Structured meshes use the single matrix of cell 0 (FEM.py:571, 757), others one per element."""
+        key = (which, coat)
+        if key not in self._E:
+            d = self.device
+            conn = d.conn[:1].contiguous() if self.mesh.structured else d.conn
+            if which == 'K':
+                T = self.coat_tensors if coat else self.tensors
+                E = elements.ke_batch_device(d.etype, self.N_dof, d.xy, conn, T)
+            else:
+                if self.V is not None and not coat:
+                    V = elements.mass_tensor(d.etype, self.N_dof, V=self.V)
+                else:
+                    mat = self.materials[1] if coat else self.materials[0]
+                    V = elements.mass_tensor(d.etype, self.N_dof, mat, self.coat_ho if coat else self.ho)
+                E = elements.me_batch_device(d.etype, self.N_dof, d.xy, conn, V)
+            self._E[key] = (E, 0 if self.mesh.structured else 1)
+        return self._E[key]
+
+    def _assemble_values(self, which, X, expo):
+        d = self.device
+        Eb, pe_b = self._element_matrices(which, False)
+        Ec, pe_c = self._element_matrices(which, True) if self.coating else (None, 0)
+        x = self._x_device(X)
+        vals = torch.empty(d.nnz, dtype=torch.float64, device=d.dev)
+        _lib.call('femol_assemble', d.plan, _lib.ptr(Eb), pe_b, _lib.ptr(Ec), pe_c, _lib.ptr(x),
+                  float(expo) if expo is not None else 1.0, _lib.ptr(self._fixed_mask()), _lib.ptr(d.xpow),
+                  _lib.ptr(vals), _lib.stream())
+        return vals
+
+    # ---- assembly -----------------------------------------------------------------------------------
+    def assemble(self, which, X=None, p=None, q=None):
+        """FEM.py:160-183.  which in 'K' | 'M' | 'F'; X = {cell_type: densities} or None."""
+        if which == 'M':
+            self._Mv = self._assemble_values('M', X, q)
+            self._M_host = None
+        elif which == 'K':
+            self.assemble('F')
+            self._Kv = self._assemble_values('K', X, p)
+            self._K_host = None
+        elif which == 'F':
+            self._assemble_F()
+
+    def _assemble_F(self):
+        """FEM.py:536-544: zero the force at fixed dofs."""
+        if self.fixed_ddls:
+            self.F[self.fixed_dofs()] = 0
+        self._F_dev = torch.from_numpy(np.ascontiguousarray(self.F, dtype=np.float64)).to(self.device.dev)
+
+    @property
+    def K(self):
+        if self._Kv is None:
+            raise AttributeError('K')
+        if self._K_host is None:
+            self._K_host = self.device.to_scipy(self._Kv)
+        return self._K_host
+
+    @property
+    def M(self):
+        if self._Mv is None:
+            raise AttributeError('M')
+        if self._M_host is None:
+            self._M_host = self.device.to_scipy(self._Mv)
+        return self._M_host
+
+    @property
+    def K_values(self):
+        """CSR values of K on the device (torch, plan order)."""
+        return self._Kv
+
+    @property
+    def M_values(self):
+        return self._Mv
+
+    # ---- solvers --------------------------------------------------------------------------------------
+    def solve(self, verbose=True, filtre=0, solve_from_zc=False, h_min=0, modal_solver='lobpcg', sigma=None):
+        """FEM.py:189-199.  displacement -> mesh (with mesh.U and point data); modal -> (f[Hz], v[k, ndof])."""
+        if solve_from_zc:
+            raise NotImplementedError('variable-core laminate re-assembly (solve_from_zc) is outside the accelerated path')
+        if self.physics == 'displacement':
+            return self._displacement_solve(verbose)
+        elif self.physics == 'modal':
+            return self._modal_solve(verbose)
+
+    def solve_device(self):
+        """K U = F on the device; returns the device displacement tensor (no host copy)."""
+        d = self.device
+        if self._Kv is None:
+            self.assemble('K')
+        if self._U_dev is None or not self.warm_start:
+            self._U_dev = torch.zeros(d.n, dtype=torch.float64, device=d.dev)
+        iters = ctypes.c_int(0)
+        relres = ctypes.c_double(0.0)
+        rc = _lib.call('femol_pcg', d.plan, _lib.ptr(self._Kv), _lib.ptr(self._F_dev), _lib.ptr(self._U_dev),
+                       float(self.solver_rtol), int(self.solver_max_iter), _PRECOND[self.preconditioner],
+                       _lib.ptr(d.pcg_ws()), ctypes.byref(iters), ctypes.byref(relres), _lib.stream())
+        self.solver_info = {'iterations': iters.value, 'relres': relres.value, 'status': rc}
+        if rc == _lib.S_BREAKDOWN:
+            raise _lib.FemolError('PCG breakdown (matrix not positive definite?) after %d iterations' % iters.value)
+        return self._U_dev
+
+    def _displacement_solve(self, verbose):
+        """FEM.py:201-214"""
+        U = self.solve_device().cpu().numpy()
+        if verbose:
+            print('Solved with femol_pcg: %(iterations)d iterations, relative residual %(relres).2e' % self.solver_info)
+        self.mesh.add_displacement(U, self.N_dof)
+        return self.mesh
+
+    def modal_device(self, k=None, X0=None):
+        """Lowest k physical eigenpairs on the device: (lambda[k] (rad/s)^2 host, V [k][n] device tensor)."""
+        d = self.device
+        if self._Mv is None:
+            self.assemble('M')
+        if self._Kv is None:
+            self.assemble('K')
+        k = k or self.n_modes
+        m = _lobpcg.pick_block_size(k)
+        mask = self._fixed_mask()
+        if X0 is None and self._X_modal is not None and self._X_modal.shape == (d.n, m) and self.warm_start:
+            X0 = self._X_modal
+        if X0 is None:
+            g = torch.Generator(device=d.dev)
+            g.manual_seed(1234)
+            X0 = torch.randn((d.n, m), dtype=torch.float64, device=d.dev, generator=g)
+        X0 = X0.clone()
+        if mask is not None:  # fixed dofs are projected out (the reference keeps them as lambda = 1 pairs)
+            bits = (mask.to(torch.int32)[:, None] >> torch.arange(self.N_dof, device=d.dev, dtype=torch.int32)[None]) & 1
+            X0[bits.reshape(-1).bool()] = 0.0
+        ops = _lobpcg.DeviceOps(d.plan, self._Kv, self._Mv, mask, m, _PRECOND[self.preconditioner], X0)
+        lam, rel, its = _lobpcg.lobpcg(ops, m, k, tol=self.modal_tol, max_iter=self.modal_max_iter)
+        V = ops.vectors()
+        self._X_modal = V.clone()
+        self.solver_info = {'iterations': its, 'relres': rel[:k].copy(), 'block': m}
+        return lam[:k], V[:, :k].t().contiguous()
+
+    def _modal_solve(self, verbose):
+        """FEM.py:216-256: returns (sqrt(lambda)/2pi [Hz], v) with v rows = M-orthonormal modes."""
+        lam, V = self.modal_device()
+        if verbose:
+            print('Solved with LOBPCG: %(iterations)d iterations' % self.solver_info)
+        w = np.sqrt(np.maximum(lam, 0.0)) / (2 * np.pi)
+        return w, V.cpu().numpy()

@@ -1,0 +1,183 @@
+"""SIMP_VIBE — eigenfrequency topology optimisation with MAC mode tracking, on the device.
+
+Mirror of the reference's FEMOL/TOM.py (`SIMP_VIBE(Problem, volfrac, p, q, rmin, FEM_solver_type)`,
+`solve(v_ref, converge, min_iter, max_iter, ...)`, attributes `lmbd, dlmbd, lmbds, v, X, change, loop`).
+One iteration (TOM.py:110-127):
+
+    K(x^p), M(x^q)               femol_assemble x2
+    lowest modes                  LOBPCG over the block kernels (was dense eigh of ALL modes, FEM.py:277)
+    mode pick by MAC vs v_ref     femol_mac + argmax                      (TOM.py:383-386)
+    dl_e                          femol_sens_eig, lambda in Hz            (TOM.py:408-495, FEM.py:256)
+    filter / OC (move 0.3)        femol_filter_* / femol_oc_update mode 1 (TOM.py:305-354, 251-303)
+
+Differences from the reference, by construction: only the `n_modes` lowest PHYSICAL modes are computed
+(the reference computes all n, including one spurious lambda = 1 pair per fixed dof); the tracked mode must
+be among them.  Save / plot / core-height post-processing are outside the accelerated path.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .TOM_SIMP import apply_filter, build_filter, domain_mask
+
+__all__ = ['SIMP_VIBE']
+
+
+class SIMP_VIBE(object):
+
+    def __init__(self, Problem, volfrac=0.5, p=3, q=1, rmin=1.5, FEM_solver_type='fast', saving_root=None):
+        self.FEM = Problem
+        self.mesh = Problem.mesh
+        self.mesh.compute_element_centers()
+        if FEM_solver_type != 'fast':
+            raise NotImplementedError("only FEM_solver_type='fast' is on the accelerated path")
+        self.FEM_solver = self._SIMP_fast_modal_solver
+        kind = 'coating' * self.FEM.coating + 'solid' * (not self.FEM.coating)
+        self.objective_function = {'solid': self._solid_max_eigs_objective_function,
+                                   'coating': self._coating_max_eigs_objective_function}[kind]
+        self.element_areas = np.hstack([self.mesh.areas[c] for c in self.mesh.contains])
+        self.mesh_area = np.sum(self.element_areas)
+        self.f, self.rmin, self.p, self.q = volfrac, rmin, p, q
+        self.X = {key: np.ones(self.mesh.cells[key].shape[0]) * volfrac for key in self.mesh.contains}
+        self.lmbds, self.all_lmbds, self.eigen_vectors, self.macs = [], [], [], []
+        self.v = 0
+        self.lmbd = 0
+        self.dlmbd = 0
+        self.loop = 0
+        self.change = None
+        self.archive = True
+        d = self.FEM.device
+        self._x = torch.full((d.n_elem,), float(volfrac), dtype=torch.float64, device=d.dev)
+        self._dl = torch.empty(d.n_elem, dtype=torch.float64, device=d.dev)
+        self._dlf = torch.empty(d.n_elem, dtype=torch.float64, device=d.dev)
+        self._xn = torch.empty(d.n_elem, dtype=torch.float64, device=d.dev)
+        self._scal = torch.zeros(8, dtype=torch.float64, device=d.dev)
+        self._lam = torch.zeros(1, dtype=torch.float64, device=d.dev)
+        self._areas = None if self.mesh.structured else torch.from_numpy(np.ascontiguousarray(self.element_areas)).to(d.dev)
+        self._filter = None
+        self._mask = None
+        self._mask_key = None
+
+    def set_density(self, X):
+        if isinstance(X, dict):
+            X = X[self.mesh.contains[0]]
+        self._x.copy_(torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64)))
+
+    def density(self):
+        return self._x.cpu().numpy()
+
+    def _SIMP_fast_modal_solver(self, X=None, v_ref=None, verbose=False):
+        """TOM.py:374-386: assemble K(x^p), M(x^q), solve, pick the mode with the best MAC to v_ref.
+        Returns (f [Hz], v (device tensor))."""
+        d = self.FEM.device
+        x = self._x if X is None else X
+        self.FEM.assemble('K', X=x, p=self.p)
+        self.FEM.assemble('M', X=x, q=self.q)
+        lam, V = self.FEM.modal_device()
+        w = np.sqrt(np.maximum(lam, 0.0)) / (2 * np.pi)
+        self.all_lmbds.append(w)
+        vr = v_ref if isinstance(v_ref, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v_ref, dtype=np.float64)).to(d.dev)
+        mac = torch.empty(V.shape[0], dtype=torch.float64, device=d.dev)
+        _lib.call('femol_mac', d.n, V.shape[0], _lib.ptr(V), _lib.ptr(vr), _lib.ptr(mac), _lib.ptr(d.red_ws), _lib.stream())
+        mac_h = mac.cpu().numpy()
+        i = int(np.argmax(mac_h))
+        self.macs.append(float(mac_h[i]))
+        if verbose:
+            print('Best mac match (LOBPCG) :', mac_h[i])
+        return w[i], V[i].contiguous()
+
+    def _objective(self, coating):
+        d = self.FEM.device
+        Ke, pe_k = self.FEM._element_matrices('K', coating)
+        Me, pe_m = self.FEM._element_matrices('M', coating)
+        structured = self.mesh.structured
+        # unstructured SOLID problems reuse the x^p / x^q scaled element matrices (FEM.py:630, 779); the
+        # unstructured coating K_coat is scaled too (FEM.py:673) but M_coat is not (FEM.py:845-849)
+        ek = self.p - 1 if structured else 2 * self.p - 1
+        em = self.q - 1 if (structured or coating) else 2 * self.q - 1
+        self._lam.fill_(float(self.lmbd))
+        _lib.call('femol_sens_eig', d.plan, _lib.ptr(Ke), pe_k, _lib.ptr(Me), pe_m, _lib.ptr(self._v), _lib.ptr(self._x),
+                  float(self.p), float(self.q), float(ek), float(em), _lib.ptr(self._lam), _lib.ptr(self._dl),
+                  _lib.stream())
+        return self.lmbd, self._dl
+
+    def _solid_max_eigs_objective_function(self, X=None):
+        """TOM.py:408-451"""
+        return self._objective(False)
+
+    def _coating_max_eigs_objective_function(self, X=None):
+        """TOM.py:453-495"""
+        return self._objective(True)
+
+    def _filter_sensibility(self, X=None):
+        """TOM.py:305-354"""
+        if self._filter is None:
+            self._filter = build_filter(self.mesh, self.rmin, self.FEM.device.dev)
+        apply_filter(self._filter, self._x, self._dl, self._dlf)
+        self._dl, self._dlf = self._dlf, self._dl
+
+    def _get_new_x(self, X=None):
+        """TOM.py:251-303 (move 0.3, negative sensitivities clamped, rescale when sum < 1)."""
+        key = (getattr(self, 'solid_domain', None), getattr(self, 'void_domain', None))
+        if key != self._mask_key:
+            self._mask = domain_mask(self.mesh, key[0], key[1], self.FEM.device.dev)
+            self._mask_key = key
+        d = self.FEM.device
+        _lib.call('femol_oc_update', d.n_elem, _lib.ptr(self._x), _lib.ptr(self._dl), 1, float(self.f),
+                  _lib.ptr(self._areas), _lib.ptr(self._mask), _lib.ptr(self._xn), self._scal.data_ptr() + 4 * 8,
+                  _lib.ptr(d.red_ws), _lib.stream())
+        return self._xn
+
+    def iterate(self, v_ref):
+        self.lmbd, self._v = self.FEM_solver(None, v_ref=v_ref, verbose=False)
+        self.lmbds.append(self.lmbd)
+        self.objective_function(None)
+        self._filter_sensibility(None)
+        self._get_new_x(None)
+        self._x, self._xn = self._xn, self._x
+        self.change = float(self._scal[4].item())
+        return self.change, self.lmbd
+
+    def check_convergence(self, converge, min_iter, max_iter, convergence_criteria):
+        """TOM.py:155-173"""
+        solved = False
+        if convergence_criteria == 'change':
+            if (self.change < converge) and (self.loop > min_iter):
+                solved = True
+        elif convergence_criteria == 'objective':
+            if np.abs(np.mean(self.lmbds[-3:-1]) - self.lmbds[-1]) < converge:
+                solved = True
+        if self.loop == max_iter:
+            solved = True
+        return solved
+
+    def solve(self, v_ref, converge=0.01, min_iter=1, max_iter=100, plot=True, save=True, verbose=True,
+              convergence_criteria='change', mesh_filename=None, eigvals_filename=None, eigvecs_filename=None):
+        """TOM.py:87-132 (`plot` / `save` ignored: matplotlib / meshio are outside the accelerated path)."""
+        self.change = 1
+        self.loop = 0
+        ctype = self.mesh.contains[0]
+        self.set_density(self.X)
+        solved = False
+        while not solved:
+            self.loop += 1
+            self.iterate(v_ref)
+            if self.archive:
+                self.X = {ctype: self.density()}
+                self.v = self._v.cpu().numpy()
+                self.eigen_vectors.append(self.v)
+                self.dlmbd = self._dl.cpu().numpy()
+                X_key = 'X{}'.format(self.loop - 1)
+                if 'X' in self.mesh.cell_data.keys():
+                    self.mesh.cell_data[X_key] = self.mesh.cell_data['X']
+                self.mesh.cell_data['X'] = self.X
+                self.mesh.add_mode('m{}'.format(self.loop), self.v, self.FEM.N_dof)
+            if verbose:
+                print(f'Iteration : {self.loop}, Variation : {self.change}, EigenVal : {self.lmbd}')
+            solved = self.check_convergence(converge, min_iter, max_iter, convergence_criteria)
+        if not self.archive:
+            self.X = {ctype: self.density()}
+            self.v = self._v.cpu().numpy()
+            self.dlmbd = self._dl.cpu().numpy()
+            self.mesh.cell_data['X'] = self.X
+        return self.mesh

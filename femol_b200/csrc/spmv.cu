@@ -1,0 +1,60 @@
+// K4: sparse matrix-vector products.
+//
+// femol_spmv: y = A x for a matrix whose values are stored in the plan's CSR order.  Column indices are
+// NOT read from the CSR `indices` array: every node pair owns a dense ndof x ndof block, so the kernel
+// reads the node adjacency (4 B per block instead of 4 B per entry) and derives the columns.  HBM
+// traffic per product: 8*nnz (values) + 4*nnz/ndof^2 (adjacency) + 16*n (x once, y once) — 25 % less
+// than plain CSR at ndof = 2 and 33 % less at ndof = 6.
+// femol_spmv_csr: plain CSR product for arbitrary matrices (parity checks against scipy matrices).
+#include "common.cuh"
+#include "spmv.cuh"
+
+namespace {
+
+template <int G>
+__global__ void __launch_bounds__(256)
+spmv_csr_kernel(int64_t n_rows, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
+    const int g = threadIdx.x % G;
+    const int64_t row0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x / G;
+    for (int64_t r = row0; r < n_rows + (G - 1); r += stride) {  // keep whole groups converged
+        double acc = 0.0;
+        if (r < n_rows) {
+            const int b = indptr[r], e = indptr[r + 1];
+            for (int c = b + g; c < e; c += G) acc += vals[c] * __ldg(&x[indices[c]]);
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (g == 0 && r < n_rows) y[r] = acc;
+    }
+}
+
+}  // namespace
+
+int femol_spmv_launch(femol_plan_t p, const double* vals, const double* x, double* y, const double* dot_with,
+                      double* dot_out, double* red_ws, cudaStream_t st) {
+    int rc = FEMOL_E_ARG;
+    if (p->ndof == 2) rc = spmv_node_launch<2>(p, vals, x, y, dot_with, dot_out, red_ws, st);
+    else if (p->ndof == 6) rc = spmv_node_launch<6>(p, vals, x, y, dot_with, dot_out, red_ws, st);
+    else femol_set_error("femol_spmv: unsupported ndof %d", p->ndof);
+    return rc;
+}
+
+extern "C" int femol_spmv(femol_plan_t p, const double* vals, const double* x, double* y, void* stream) {
+    FEMOL_REQUIRE(p && vals && x && y, "femol_spmv: null argument");
+    return femol_spmv_launch(p, vals, x, y, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int femol_spmv_csr(int64_t n_rows, const int32_t* indptr, const int32_t* indices, const double* vals,
+                              const double* x, double* y, void* stream) {
+    FEMOL_REQUIRE(indptr && indices && vals && x && y && n_rows >= 0, "femol_spmv_csr: bad argument");
+    if (n_rows == 0) return FEMOL_OK;
+    constexpr int G = 8;
+    int64_t blocks = (n_rows * G + 255) / 256;
+    const int64_t cap = (int64_t)femol_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    spmv_csr_kernel<G><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n_rows, indptr, indices, vals, x, y);
+    FEMOL_LAUNCH_CHECK();
+    return FEMOL_OK;
+}

@@ -1,0 +1,74 @@
+// Node-block SpMV kernel shared by the PCG and LOBPCG drivers (see spmv.cu for the traffic model).
+#pragma once
+#include "common.cuh"
+
+// One group of G lanes per CSR row; the row's values are read as a contiguous double2 stream with
+// streaming (evict-first) loads so that the L2 stays available for the gathered x vector; x is read
+// through the read-only path as double2 (two dofs of one neighbour node per load).
+// Optional fused dot product: dot_out[0] = sum_r y[r] * dot_with[r] (deterministic grid reduction).
+template <int ND, int G>
+__global__ void __launch_bounds__(256)
+spmv_node_kernel(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx,
+                 const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                 const double* __restrict__ dot_with, double* __restrict__ dot_out, double* __restrict__ red_ws) {
+    static_assert(ND % 2 == 0, "ndof must be even for the double2 path");
+    constexpr int H = ND / 2;  // double2 pairs per neighbour node
+    __shared__ double s_red[32];
+    const int g = threadIdx.x % G;
+    const int64_t n_rows = n_nodes * ND;
+    const int64_t row0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x / G;
+    const int64_t n_iter = (n_rows + stride - 1) / stride;
+    const double2* __restrict__ x2 = reinterpret_cast<const double2*>(x);
+    double dot[1] = {0.0};
+    for (int64_t it = 0; it < n_iter; ++it) {
+        const int64_t r = row0 + it * stride;
+        double acc = 0.0;
+        if (r < n_rows) {
+            const int64_t i = r / ND;
+            const int da = (int)(r - i * ND);
+            const int pb = __ldg(&adj_ptr[i]);
+            const int len = __ldg(&adj_ptr[i + 1]) - pb;
+            const int64_t base2 = ((int64_t)ND * ND * pb + (int64_t)da * len * ND) >> 1;
+            const double2* __restrict__ v2 = reinterpret_cast<const double2*>(vals) + base2;
+            const int n2 = len * H;
+            for (int c = g; c < n2; c += G) {
+                const int k = c / H, h = c - k * H;
+                const int32_t j = __ldg(&adj_idx[pb + k]);
+                const double2 a = __ldcs(&v2[c]);
+                const double2 b = __ldg(&x2[(int64_t)j * H + h]);
+                acc += a.x * b.x;
+                acc += a.y * b.y;
+            }
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (g == 0 && r < n_rows) {
+            y[r] = acc;
+            if (dot_with) dot[0] += acc * dot_with[r];
+        }
+    }
+    if (dot_out) {
+        unsigned long long* ticket = reinterpret_cast<unsigned long long*>(red_ws + FEMOL_RED_CHANNELS * FEMOL_RED_MAX_BLOCKS);
+        grid_sum_finish<1>(dot, red_ws, ticket, dot_out, s_red);
+    }
+}
+
+template <int ND>
+int spmv_node_launch(femol_plan_t p, const double* vals, const double* x, double* y, const double* dot_with,
+                     double* dot_out, double* red_ws, cudaStream_t st) {
+    constexpr int G = ND == 2 ? 4 : 8;
+    const int64_t n_rows = p->n_nodes * ND;
+    int64_t blocks = (n_rows * G + 255) / 256;
+    int64_t cap = (int64_t)p->sm_count * 8;
+    if (cap > FEMOL_RED_MAX_BLOCKS) cap = FEMOL_RED_MAX_BLOCKS;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    spmv_node_kernel<ND, G><<<(int)blocks, 256, 0, st>>>(p->n_nodes, p->adj_ptr, p->adj_idx, vals, x, y, dot_with,
+                                                          dot_out, red_ws);
+    FEMOL_LAUNCH_CHECK();
+    return FEMOL_OK;
+}
+
+int femol_spmv_launch(femol_plan_t p, const double* vals, const double* x, double* y, const double* dot_with,
+                      double* dot_out, double* red_ws, cudaStream_t st);

@@ -1,0 +1,189 @@
+/* femol_b200 — C-ABI of the B200-native FEMOL hot path (sm_100a).
+ *
+ * Drop-in boundary.  The reference (olivecha/FEMOL) is pure Python and has no
+ * FFI; the seams this library is bound behind are the Python methods cited on each entry point.
+ * The host-side mirror of those methods lives in `femol_b200/` (Python, like the reference) and
+ * calls these functions through ctypes; INTEGRATION.md shows the stub a FEMOL maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory (torch tensors in our host code)
+ *     unless the parameter name starts with `h_` (host pointer, written synchronously);
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous w.r.t. the host unless
+ *     the function returns host scalars (`h_*`), in which case it synchronises that stream;
+ *   - return value: 0 = ok; <0 = error (FEMOL_E_*; FEMOL_E_CUDA: see femol_last_error());
+ *     >0 = solver status (FEMOL_S_*);
+ *   - no exceptions cross the boundary; no global mutable state besides the last-error string;
+ *   - a plan may be used from one stream at a time;
+ *   - doubles are IEEE FP64, indices are int32 (as scipy CSR), element/node counts are int64;
+ *   - element matrices are row-major, node-major / dof-minor, dofs (Ux,Uy,Uz,Tx,Ty,Tz)
+ *     (reference mesh.py:17, 297-301).
+ */
+#ifndef FEMOL_B200_H
+#define FEMOL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEMOL_OK 0
+#define FEMOL_E_ARG (-1)      /* bad argument */
+#define FEMOL_E_CUDA (-2)     /* CUDA runtime / launch failure */
+#define FEMOL_E_LIMIT (-3)    /* mesh exceeds a compiled limit (node valence, row length) */
+#define FEMOL_E_NOGPU (-4)    /* no CUDA device */
+#define FEMOL_S_NOT_CONVERGED 1
+#define FEMOL_S_BREAKDOWN 2   /* PCG/LOBPCG breakdown (p'Ap <= 0 or NaN) */
+
+/* element types: reference FEMOL/elements.py classes T3 :43, T6 :277, Q4 :686, Q8 :1156 */
+#define FEMOL_T3 0
+#define FEMOL_Q4 1
+#define FEMOL_T6 2
+#define FEMOL_Q8 3
+
+/* preconditioners for femol_pcg / femol_lobpcg */
+#define FEMOL_PRECOND_NONE 0
+#define FEMOL_PRECOND_JACOBI 1
+#define FEMOL_PRECOND_BLOCK_JACOBI 2 /* ndof x ndof node blocks */
+
+typedef struct femol_plan* femol_plan_t;
+
+const char* femol_last_error(void);
+const char* femol_version(void);
+int femol_device_count(void);
+/* number of femol kernels launched by this process so far (optionally reset); bench.py reports it */
+int64_t femol_launch_count(int reset);
+
+/* ---- K1/K2: batched element matrices --------------------------------------------------------
+ * Replaces Element.Ke(*tensors) (elements.py:218-239 T3, 560-621 T6, 987-1072 Q4, Q8 stub 1351) and
+ * Element.Me(material, thickness[, V]) (elements.py:241-274, 623-683, 1074-1142), evaluated for a
+ * batch of elements.  xy: [n_nodes][2]; conn: [n_elem][nn].
+ * tensors: 31 doubles = A(3x3) | D(3x3) | G(2x2) | B(3x3) row-major (plane stress uses A only).
+ * V: ndof x ndof mass tensor (the T6 0.45/0.5 factors, elements.py:649,673, are folded in by the host).
+ * out: [n_elem][size][size], size = nn*ndof. */
+int femol_ke_batch(int etype, int ndof, int64_t n_elem, const double* xy, const int32_t* conn,
+                   const double* tensors, double* ke_out, void* stream);
+int femol_me_batch(int etype, int ndof, int64_t n_elem, const double* xy, const int32_t* conn,
+                   const double* V, double* me_out, void* stream);
+
+/* ---- symbolic plan: sparsity pattern + element<->CSR maps -----------------------------------
+ * Replaces Mesh.global_matrix_indexes (mesh.py:284-308) + the pattern part of
+ * csr_matrix(...).sum_duplicates() (FEM.py:498-501): sorted int32 indices, explicit zeros kept,
+ * pattern = mesh connectivity x ndof^2.  The plan copies `conn` and owns the node adjacency and the
+ * node->element incidence; CSR arrays are exported into caller-owned buffers. */
+int femol_plan_create(int64_t n_elem, int nn, int ndof, int64_t n_nodes, const int32_t* conn,
+                      void* stream, femol_plan_t* plan_out);
+int femol_plan_destroy(femol_plan_t plan);
+/* h_info[0]=nnz_node, [1]=nnz (= ndof^2 * nnz_node), [2]=max node valence, [3]=max nodes per row,
+ * [4]=n_elem, [5]=n_nodes, [6]=nn, [7]=ndof */
+int femol_plan_info(femol_plan_t plan, int64_t* h_info);
+int femol_plan_export_csr(femol_plan_t plan, int32_t* indptr, int32_t* indices, void* stream);
+/* node adjacency (block-CSR view of the same pattern): adj_ptr [n_nodes+1], adj_idx [nnz_node] */
+int femol_plan_export_adjacency(femol_plan_t plan, int32_t* adj_ptr, int32_t* adj_idx, void* stream);
+/* element -> CSR scatter map: map[e][a][b] = node-block position of (conn[e][a], conn[e][b]) in
+ * adj_idx; the CSR position of dof pair (da,db) is indptr[node_a*ndof+da] + rank*ndof + db. */
+int femol_plan_export_scatter_map(femol_plan_t plan, int32_t* map, void* stream);
+
+/* ---- K3: numeric assembly with fused SIMP scaling and boundary conditions --------------------
+ * Replaces _K/_M_*_mesh_data_* (FEM.py:550-695, 737-871), _apply_boundary_conditions_to_matrix_data
+ * (FEM.py:902-930) and the value part of csr_matrix + sum_duplicates (FEM.py:498-501, 532-534).
+ *   solid   (e_coat == NULL):  vals = sum_e  x_e^expo * E_e
+ *   coating (e_coat != NULL):  vals = sum_e (E_e + x_e^expo * Ecoat_e)
+ * x == NULL means no scaling.  e_base/e_coat are one size x size matrix (per_elem = 0: structured
+ * mesh, every element equal) or [n_elem][size][size] (per_elem = 1).  fixed: [n_nodes] bytes, bit d of
+ * fixed[node] set = dof d of that node is a Dirichlet dof (row and column zeroed, diagonal set to 1);
+ * may be NULL.
+ * xpow_ws: n_elem doubles of workspace (receives x^expo).  vals: [nnz], fully overwritten. */
+int femol_assemble(femol_plan_t plan, const double* e_base, int base_per_elem, const double* e_coat,
+                   int coat_per_elem, const double* x, double expo, const uint8_t* fixed,
+                   double* xpow_ws, double* vals, void* stream);
+
+/* ---- K4: SpMV ------------------------------------------------------------------------------- */
+/* y = A x with A's values in plan CSR order, using the node-block adjacency for column indices */
+int femol_spmv(femol_plan_t plan, const double* vals, const double* x, double* y, void* stream);
+/* generic CSR (any matrix, e.g. a scipy one) */
+int femol_spmv_csr(int64_t n_rows, const int32_t* indptr, const int32_t* indices, const double* vals,
+                   const double* x, double* y, void* stream);
+
+/* ---- K5: preconditioned conjugate gradients (replaces spsolve, FEM.py:258-265) --------------
+ * Solves A u = f from the initial guess in u.  ws: femol_pcg_workspace_doubles(plan) doubles.
+ * Stops when ||r|| <= rtol*||f|| (recurrence residual; the true residual is re-checked and the
+ * recurrence restarted if it drifted).  h_iters / h_relres receive the iteration count and the final
+ * TRUE relative residual ||f - A u|| / ||f||. */
+int64_t femol_pcg_workspace_doubles(femol_plan_t plan);
+int femol_pcg(femol_plan_t plan, const double* vals, const double* f, double* u, double rtol,
+              int max_iter, int precond, double* ws, int* h_iters, double* h_relres, void* stream);
+
+/* ---- K6: block kernels for LOBPCG (replaces the dense eigh(K, M) of FEM.py:277 / eigsh of FEM.py:234) ----
+ * The Rayleigh-Ritz outer iteration (3m x 3m pencil, m <= 16) is host logic (femol_b200/lobpcg.py); all
+ * O(n) work is here.  Block vectors are row-major [n][ld] (the m values of one dof contiguous).
+ *   femol_spmm            Y[:, :m] = A X[:, :m]   (matrix values read once for the m vectors; m in 1,2,4,8,12,16)
+ *   femol_gram            out[qa][qb] = A^T B over n rows (deterministic); ws: femol_gram_workspace_doubles(qa,qb)
+ *   femol_block_gemm      Y[n][mc] = alpha S[n][q] C[q][mc] + beta Y   (C: device, row-major; Y may alias
+ *                         columns of S over the same rows)
+ *   femol_block_residual  R = KX - MX diag(lambda)             (lambda: device [m])
+ *   femol_precond_setup   dinv[n_nodes][ndof][ndof] = inverse of diag / diagonal blocks / identity
+ *   femol_precond_apply   W = dinv R with fixed dofs (node bit mask, as femol_assemble) zeroed */
+int femol_spmm(femol_plan_t plan, const double* vals, const double* X, int ldx, double* Y, int ldy, int m,
+               void* stream);
+int64_t femol_gram_workspace_doubles(int qa, int qb);
+int femol_gram(int64_t n, int qa, int qb, const double* A, int lda, const double* B, int ldb, double* out,
+               double* ws, void* stream);
+int femol_block_gemm(int64_t n, int q, int mc, const double* S, int lds, const double* C, double* Y, int ldy,
+                     double alpha, double beta, void* stream);
+int femol_block_residual(int64_t n, int m, const double* KX, int ldk, const double* MX, int ldm,
+                         const double* lambda, double* R, int ldr, void* stream);
+int femol_precond_setup(femol_plan_t plan, const double* vals, int kind, double* dinv, void* stream);
+int femol_precond_apply(femol_plan_t plan, const double* dinv, const uint8_t* fixed, const double* R, int ldr,
+                        double* W, int ldw, int m, void* stream);
+
+/* ---- K7/K8: element sensitivities -----------------------------------------------------------
+ * compliance (TOM_SIMP.py:126-226):  q_e = u_e' E_e u_e (and qc_e with Ecoat)
+ *   solid:   c = sum x^pc q ;           dc_e = -p x^pd q
+ *   coating: c = sum (q + x^pc qc) ;    dc_e = -p x^pd qc
+ * pc/pd are passed explicitly: structured pc = p, pd = p-1; unstructured pc = 2p, pd = 2p-1 (the
+ * reference re-uses the already penalised element matrices, FEM.py:630-631, 673-675).
+ * c_out: device scalar.  ws: femol_reduce_workspace_doubles() doubles. */
+int64_t femol_reduce_workspace_doubles(void);
+int femol_sens_compliance(femol_plan_t plan, const double* e_base, int base_per_elem, const double* e_coat,
+                          int coat_per_elem, const double* u, const double* x, double p, double pc,
+                          double pd, double* dc_out, double* c_out, double* ws, void* stream);
+/* eigenvalue (TOM.py:408-495): dl_e = v_e'(p x^ek K_e - lambda q x^em M_e) v_e ; structured ek = p-1,
+ * em = q-1 ; unstructured ek = 2p-1, em = 2q-1.  lambda: device scalar pointer (Hz, FEM.py:256). */
+int femol_sens_eig(femol_plan_t plan, const double* ke, int ke_per_elem, const double* me, int me_per_elem,
+                   const double* v, const double* x, double p, double q, double ek, double em,
+                   const double* lambda, double* dl_out, void* stream);
+
+/* ---- K9: mesh-independency filter (TOM_SIMP.py:228-277 == TOM.py:305-354) --------------------
+ * out_i = sum_{j != i} H_ij x_j dc_j / (x_i sum_{j != i} H_ij),  H_ij = max(0, rmin - d_ij / h).
+ * grid: structured mesh, element e = i*n_fast + j; w: [(2rx+1)][(2ry+1)] weight table (centre = 0).
+ * list: general neighbour list (CSR) with weights. */
+int femol_filter_grid(int64_t n_slow, int64_t n_fast, int rx, int ry, const double* w, const double* x,
+                      const double* dc, double* out, void* stream);
+int femol_filter_list(int64_t n_elem, const int32_t* nbr_ptr, const int32_t* nbr_idx, const double* nbr_w,
+                      const double* x, const double* dc, double* out, void* stream);
+
+/* ---- K10: optimality-criteria update with device-side bisection ------------------------------
+ * mode 0 = SIMP_COMP._get_new_x (TOM_SIMP.py:279-313): move 0.5, sign convention switched by any(dc>0)
+ * mode 1 = SIMP_VIBE._get_new_x (TOM.py:251-303): move 0.3, dl<0 -> 0, rescale by 1/max if sum(dl) < 1
+ *          (dc is modified in place like the reference's self.dlmbd)
+ * areas: NULL -> volume test by count (sum x - f N > 0), else area weighted (TOM.py:294).
+ * mask: per element 0 = free, 1 = solid (x=1), 2 = void (x=0.001); may be NULL.
+ * scalars_out (device, 4 doubles): [0] change = max|x_new - x|, [1] sum(x_new), [2] last lmid, [3] #bisections.
+ * ws: femol_reduce_workspace_doubles() doubles. */
+int femol_oc_update(int64_t n_elem, const double* x, double* dc, int mode, double volfrac,
+                    const double* areas, const uint8_t* mask, double* x_new, double* scalars_out,
+                    double* ws, void* stream);
+
+/* ---- K11: modal assurance criterion (utils.py:436-447; TOM.py:383-386) ----------------------
+ * mac_out[i] = (V_i . v_ref)^2 / ((V_i . V_i)(v_ref . v_ref)), V: [k][n] row-major; device output [k]. */
+int femol_mac(int64_t n, int k, const double* V, const double* v_ref, double* mac_out, double* ws,
+              void* stream);
+
+/* ---- small vector helpers used by the host mirror (all device pointers) ---------------------- */
+int femol_dot(int64_t n, const double* a, const double* b, double* out, double* ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMOL_B200_H */

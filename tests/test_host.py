@@ -1,0 +1,165 @@
+"""Host-side logic and the C-ABI surface, without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+import femol_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports every function include/femol_b200.h declares."""
+    from femol_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'femol_b200.h')).read()
+    declared = set(re.findall(r'\b(femol_[a-z0-9_]+)\s*\(', header))
+    declared -= {'femol_plan'}
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [name for name in sorted(declared) if not hasattr(lib, name)]
+    assert not missing, missing
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert b'sm_100a' in _lib.load().femol_version()
+    assert _lib.load().femol_reduce_workspace_doubles() > 0
+
+
+def test_no_cpu_fallback():
+    """Compute entry points fail loudly without a CUDA device."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import femol_b200 as F
+    mesh = F.mesh.rectangle_Q4(4, 2, 4, 2)
+    p = F.FEM_Problem('displacement', 'plane', mesh)
+    p.define_materials(F.materials.general_isotropic())
+    p.define_tensors(1)
+    with pytest.raises(F._lib.FemolError):
+        p.assemble('K')
+    with pytest.raises(F._lib.FemolError):
+        F.elements.Q4(np.array([[0, 0], [1, 0], [1, 1], [0, 1.]]), 2).Ke(np.eye(3))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'femol_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert 'femol_oracle' not in text and 'import oracle' not in text and '/root/reference' not in text, f
+
+
+def test_laminate_tensors_match_reference(golden):
+    import femol_b200 as F
+    g = golden('laminate_tensors')
+    specs = [('general_carbon', [0, 90, 45, -45], True, 0, 0), ('general_carbon', [45, 45], True, 0, 0),
+             ('T300_N5208', [0, 0, 0, 20, -20, 90], True, 0, 0.01), ('T300_N5208', [0, 0, 0, 20, -20, 90], False, 0, 0),
+             ('general_flax', [0, 90, 0, 90], True, 0, 0), ('general_carbon', [0, 90], False, 0.002, 0),
+             ('abaqus_benchmark', [0, 90, 0, 90, 0, 90, 0], False, 0, 0), ('AS4_PEEK', [10, -35, 60], True, -0.001, 0)]
+    for i, (m, plies, sym, zc, hc) in enumerate(specs):
+        L = F.laminate.Layup(getattr(F.materials, m)(), plies=plies, symetric=sym, z_core=zc, h_core=hc)
+        for k in 'ABDG':
+            assert np.array_equal(getattr(L, k + '_mat'), g[k + str(i)]), (i, k)
+        assert L.hA == g['hA%d' % i] and np.array_equal(L.z_values, g['z%d' % i])
+
+
+@pytest.mark.parametrize('name', list(cases.CASES))
+def test_mesh_and_problem_setup_match_reference(golden, name):
+    """points, cells (incl. the T6 mid-node numbering), tensors, fixed dofs and F of every case."""
+    import femol_b200 as F
+    case, g = cases.CASES[name], golden(name)
+    problem = cases.build_problem(F, case)
+    mesh = problem.mesh
+    assert np.array_equal(mesh.points, g['points'])
+    assert np.array_equal(mesh.cells[mesh.contains[0]], g['cells'])
+    for k, T in enumerate(problem.tensors):
+        assert np.array_equal(np.asarray(T, float), g['T%d' % k])
+    if problem.coating:
+        for k, T in enumerate(problem.coat_tensors):
+            assert np.array_equal(np.asarray(T, float), g['Tc%d' % k])
+    arr = o.case_arrays(case, cases.jitter_points)
+    assert np.array_equal(problem.fixed_dofs(), arr['fixed_idx'])
+    if 'F' in g:
+        Fv = problem.F.copy(); Fv[problem.fixed_dofs()] = 0
+        assert np.array_equal(Fv, g['F'])
+
+
+def test_mesh_helpers():
+    import femol_b200 as F
+    m = F.mesh.rectangle_Q4(6., 3., 12, 6)
+    assert m.structured and m.N_ele == 72 and m.N_nodes == 13 * 7
+    assert np.isclose(m.element_size(), 0.5)
+    assert np.allclose(m.areas['quad'], 0.25)
+    assert np.allclose(m.all_cell_centers[0], [0.25, 0.25]) and np.allclose(m.all_cell_centers[1], [0.25, 0.75])
+    m.global_matrix_indexes(2)
+    r, c = o.coo_pattern(m.cells['quad'], 2)
+    assert np.array_equal(m.rows, r) and np.array_equal(m.cols, c)
+    # unused nodes are dropped and cells renumbered (mesh.py:209-240)
+    pts = np.array([[9., 9.], [0, 0], [1, 0], [1, 1], [0, 1]])
+    mm = F.Mesh(pts, {'quad': np.array([[1, 2, 3, 4]])}, quad_element=F.elements.Q4)
+    assert mm.N_nodes == 4 and np.array_equal(mm.cells['quad'], [[0, 1, 2, 3]])
+    # inverted quads are flipped (mesh.py:105-109)
+    mm = F.Mesh(pts[1:], {'quad': np.array([[0, 3, 2, 1]])}, quad_element=F.elements.Q4)
+    assert (mm.areas['quad'] > 0).all()
+    # scalar (reference-style) and vectorised domain predicates agree
+    dom = F.domains.inside_box([0], [[0, 1.5]])
+    scalar = lambda x, y: dom(x, y)
+    assert np.array_equal(m.domain_nodes(dom), m.domain_nodes(scalar))
+    assert dom(0.0, 1.0) is True and dom(1.0, 1.0) is False
+
+
+def test_filter_stencil_construction():
+    import torch
+    import femol_b200 as F
+    from femol_b200.TOM_SIMP import build_filter
+    m = F.mesh.rectangle_Q4(8., 3., 16, 6)   # h = 0.5
+    f = build_filter(m, 1.5, torch.device('cpu'))
+    assert f['kind'] == 'grid' and (f['n_slow'], f['n_fast'], f['rx'], f['ry']) == (16, 6, 1, 1)
+    w = f['w'].numpy()
+    assert w[1, 1] == 0 and np.isclose(w[0, 1], 0.5) and np.isclose(w[0, 0], 1.5 - np.sqrt(2))
+    # stencil == literal reference filter
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0.01, 1, m.N_ele); dc = -rng.uniform(0, 1, m.N_ele)
+    ref = o.filter_sens_literal(x, dc, m.all_cell_centers, 1.5, m.element_size())
+    X = x.reshape(16, 6); D = (x * dc).reshape(16, 6)
+    num = np.zeros((16, 6)); den = np.zeros((16, 6))
+    for di in (-1, 0, 1):
+        for dj in (-1, 0, 1):
+            ww = w[di + 1, dj + 1]
+            for i in range(16):
+                for j in range(6):
+                    if 0 <= i + di < 16 and 0 <= j + dj < 6:
+                        num[i, j] += ww * D[i + di, j + dj]; den[i, j] += ww
+    assert np.allclose((num / (X * den)).reshape(-1), ref, rtol=1e-13)
+    ft = build_filter(F.mesh.rectangle_T3(4., 2., 4, 2), 1.5, torch.device('cpu'))
+    assert ft['kind'] == 'list'
+
+
+def test_lobpcg_driver_on_numpy_ops(golden):
+    """The LOBPCG outer iteration (femol_b200/lobpcg.py) against the dense generalised eigen-solve."""
+    from femol_b200.lobpcg import lobpcg, pick_block_size
+    from numpy_ops import NumpyOps
+    case = cases.CASES['modal_q4_plate_ss_8x8']
+    arr = o.case_arrays(case)
+    K = o.global_matrices(arr, 'K'); M = o.global_matrices(arr, 'M')
+    w_ref, _ = o.modal_solve_dense(K, M)
+    w_ref = w_ref[np.abs(w_ref - 1 / (2 * np.pi)) > 1e-3]
+    k = 6
+    m = pick_block_size(k)
+    assert m == 8
+    X0 = np.random.default_rng(0).standard_normal((K.shape[0], m))
+    ops = NumpyOps(K, M, arr['fixed_idx'], m, X0, precond='exact')
+    lam, rel, its = lobpcg(ops, m, k, tol=1e-9, max_iter=60)
+    assert np.all(rel[:k] <= 1e-9) and its < 40, (its, rel)
+    f = np.sqrt(lam[:k]) / (2 * np.pi)
+    assert np.allclose(f, w_ref[:k], rtol=1e-7), (f, w_ref[:k])
+    V = ops.vectors()[:, :k]
+    assert np.allclose(V.T @ (M @ V), np.eye(k), atol=1e-8)      # M-orthonormal like the reference (test_modal_solver.py:7-22)
+    assert np.abs(V[arr['fixed_idx']]).max() == 0
+    # the Jacobi-preconditioned iteration converges too (slowly: the Mindlin plate pencil is stiff)
+    ops = NumpyOps(K, M, arr['fixed_idx'], m, X0, precond='jacobi')
+    lam, rel, its = lobpcg(ops, m, k, tol=1e-6, max_iter=1500)
+    assert np.all(rel[:k] <= 1e-6), (its, rel)
+    assert np.allclose(np.sqrt(lam[:k]) / (2 * np.pi), w_ref[:k], rtol=1e-6)
