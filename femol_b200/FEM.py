@@ -128,7 +128,14 @@ class FEM_Problem(object):
         self.warm_start = True
         self.n_modes = 10
         self.modal_tol = 1e-8
-        self.modal_max_iter = 2000
+        self.modal_max_iter = 500
+        self.modal_inner_iters = 200     # block-CG iterations on K per LOBPCG preconditioner application
+        self.modal_inner_tol = 1e-3
+        # Reissner-Mindlin drilling rotations: K_tz is the diagonal set to 1 per element (elements.py:1071)
+        # and the consistent mass couples tz only with tz, so the pencil has one exactly decoupled pure-tz
+        # mode per free node (a dense cluster of spurious low frequencies).  They are projected out of the
+        # LOBPCG iteration, like the lambda = 1 pairs of the fixed dofs.
+        self.deflate_drilling = True
         self.solver_info = {}
         self._dev = None
         self._E = {}          # cached element matrices on the device
@@ -328,7 +335,10 @@ class FEM_Problem(object):
         rc = _lib.call('femol_pcg', d.plan, _lib.ptr(self._Kv), _lib.ptr(self._F_dev), _lib.ptr(self._U_dev),
                        float(self.solver_rtol), int(self.solver_max_iter), _PRECOND[self.preconditioner],
                        _lib.ptr(d.pcg_ws()), ctypes.byref(iters), ctypes.byref(relres), _lib.stream())
-        self.solver_info = {'iterations': iters.value, 'relres': relres.value, 'status': rc}
+        # status 0: converged to rtol; 3: recurrence converged and the TRUE residual sits at its attainable
+        # floor (~ eps * cond(K), the level a direct solver reaches too); 1: iteration limit
+        self.solver_info = {'iterations': iters.value, 'relres': relres.value, 'status': rc,
+                            'converged': rc in (0, _lib.S_STAGNATED)}
         if rc == _lib.S_BREAKDOWN:
             raise _lib.FemolError('PCG breakdown (matrix not positive definite?) after %d iterations' % iters.value)
         return self._U_dev
@@ -351,6 +361,9 @@ class FEM_Problem(object):
         k = k or self.n_modes
         m = _lobpcg.pick_block_size(k)
         mask = self._fixed_mask()
+        if self.N_dof == 6 and self.deflate_drilling:
+            drill = torch.full((d.n_nodes,), 1 << 5, dtype=torch.uint8, device=d.dev)
+            mask = drill if mask is None else (mask | drill)
         if X0 is None and self._X_modal is not None and self._X_modal.shape == (d.n, m) and self.warm_start:
             X0 = self._X_modal
         if X0 is None:
@@ -361,7 +374,8 @@ class FEM_Problem(object):
         if mask is not None:  # fixed dofs are projected out (the reference keeps them as lambda = 1 pairs)
             bits = (mask.to(torch.int32)[:, None] >> torch.arange(self.N_dof, device=d.dev, dtype=torch.int32)[None]) & 1
             X0[bits.reshape(-1).bool()] = 0.0
-        ops = _lobpcg.DeviceOps(d.plan, self._Kv, self._Mv, mask, m, _PRECOND[self.preconditioner], X0)
+        ops = _lobpcg.DeviceOps(d.plan, self._Kv, self._Mv, mask, m, _PRECOND[self.preconditioner], X0,
+                                inner_iters=self.modal_inner_iters, inner_tol=self.modal_inner_tol)
         lam, rel, its = _lobpcg.lobpcg(ops, m, k, tol=self.modal_tol, max_iter=self.modal_max_iter)
         V = ops.vectors()
         self._X_modal = V.clone()

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libfemol_b200.so')
 T3, Q4, T6, Q8 = 0, 1, 2, 3
 ETYPE_NODES = {T3: 3, Q4: 4, T6: 6, Q8: 8}
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI = 0, 1, 2
-S_NOT_CONVERGED, S_BREAKDOWN = 1, 2
+S_NOT_CONVERGED, S_BREAKDOWN, S_STAGNATED = 1, 2, 3
 
 c_int, c_i64, c_dbl, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 P = c_vp  # every device pointer / stream / plan handle crosses as void*
@@ -45,6 +45,8 @@ SIGNATURES = {
     'femol_block_residual': (c_int, [c_i64, c_int, P, c_int, P, c_int, P, P, c_int, P]),
     'femol_precond_setup': (c_int, [P, P, c_int, P, P]),
     'femol_precond_apply': (c_int, [P, P, P, P, c_int, P, c_int, c_int, P]),
+    'femol_block_pcg_workspace_doubles': (c_i64, [P, c_int]),
+    'femol_block_pcg': (c_int, [P, P, P, P, P, c_int, P, c_int, c_int, c_int, c_dbl, P, P]),
     'femol_reduce_workspace_doubles': (c_i64, []),
     'femol_sens_compliance': (c_int, [P, P, c_int, P, c_int, P, P, c_dbl, c_dbl, c_dbl, P, P, P, P]),
     'femol_sens_eig': (c_int, [P, P, c_int, P, c_int, P, P, c_dbl, c_dbl, c_dbl, c_dbl, P, P, P]),

@@ -182,8 +182,10 @@ ke_batch_kernel(int64_t n_elem, const double* __restrict__ xy, const int32_t* __
             if (r < 3 && c < 3) v = tens[r * 3 + c];                          // A
             else if (r >= 3 && r < 6 && c >= 3 && c < 6) v = tens[9 + (r - 3) * 3 + (c - 3)];  // D
             else if (r >= 6 && c >= 6) v = tens[18 + (r - 6) * 2 + (c - 6)];  // G
-            else if (r < 3 && c >= 3 && c < 6) v = tens[22 + r * 3 + (c - 3)];  // B coupling (elements.py:1038)
-            else if (r >= 3 && r < 6 && c < 3) v = tens[22 + (r - 3) * 3 + c];  // (elements.py:1039)
+            // membrane-bending coupling B (elements.py:1038-1039); the reference's T6 plate ignores it
+            // (elements.py:587-621)
+            else if (ET != FEMOL_T6 && r < 3 && c >= 3 && c < 6) v = tens[22 + r * 3 + (c - 3)];
+            else if (ET != FEMOL_T6 && r >= 3 && r < 6 && c < 3) v = tens[22 + (r - 3) * 3 + c];
         }
         sC[i] = v;
     }

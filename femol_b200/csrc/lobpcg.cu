@@ -201,7 +201,7 @@ __global__ void precond_setup_kernel(int64_t n_nodes, const int32_t* __restrict_
 template <int ND>
 __global__ void __launch_bounds__(256)
 precond_apply_kernel(int64_t n_nodes, int m, const double* __restrict__ dinv, const uint8_t* __restrict__ fixed,
-                     const double* __restrict__ R, int ldr, double* __restrict__ W, int ldw) {
+                     const double* R, int ldr, double* W, int ldw) {  // W may alias R
     const int64_t total = n_nodes * m;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = t / m;
@@ -293,4 +293,208 @@ extern "C" int femol_precond_apply(femol_plan_t p, const double* dinv, const uin
     else { femol_set_error("femol_precond_apply: unsupported ndof %d", p->ndof); return FEMOL_E_ARG; }
     FEMOL_LAUNCH_CHECK();
     return FEMOL_OK;
+}
+
+// =====================================================================================================
+// Block PCG: W ~= K^-1 R for m right-hand sides at once (the LOBPCG preconditioner "T ~ K^-1").
+// Every column runs its own CG recurrence (alpha_c, beta_c) on the shared SpMM, preconditioned with the
+// block-Jacobi inverse.  All scalars live on the device; a fixed number of iterations is enqueued with no
+// host synchronisation; a column freezes (alpha = 0) once its preconditioned residual dropped by rel_tol.
+// Six launches per iteration: spmm, dots, scalars, update(+dots), scalars, direction.
+// =====================================================================================================
+namespace {
+
+constexpr int BP_MAXM = 16;
+constexpr int BP_BLOCKS = 592;  // 4 CTAs per SM on 148 SMs
+
+// partial[blockIdx][c] = sum over this block's rows of A[r][c] * B[r][c]
+__global__ void __launch_bounds__(256)
+bp_dots_kernel(int64_t n, int m, const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ partial) {
+    __shared__ double sh[256];
+    const int c = threadIdx.x % m;
+    const int lanes = (256 / m) * m;          // threads that own a column
+    double acc = 0.0;
+    if ((int)threadIdx.x < lanes) {
+        const int64_t r0 = (int64_t)blockIdx.x * (lanes / m) + threadIdx.x / m;
+        const int64_t stride = (int64_t)gridDim.x * (lanes / m);
+        for (int64_t r = r0; r < n; r += stride) acc += A[r * m + c] * B[r * m + c];
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if ((int)threadIdx.x < m) {
+        double s = 0.0;
+        for (int t = threadIdx.x; t < lanes; t += m) s += sh[t];
+        partial[(int64_t)blockIdx.x * m + threadIdx.x] = s;
+    }
+}
+
+// sc layout (per column c): rz[c] | pq[c] | alpha[c] | beta[c] | rz0[c] | active[c]
+enum { BP_RZ = 0, BP_PQ = 1, BP_ALPHA = 2, BP_BETA = 3, BP_RZ0 = 4, BP_ACTIVE = 5, BP_NS = 6 };
+
+// phase 0: rz0 = rz = sum ; phase 1: pq = sum, alpha = rz/pq ; phase 2: rz_new = sum, beta = rz_new/rz, rz = rz_new
+__global__ void bp_scalars_kernel(int nblk, int m, int phase, double tol2, const double* __restrict__ partial,
+                                  double* __restrict__ sc) {
+    const int c = threadIdx.x;
+    if (c >= m) return;
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += partial[(int64_t)b * m + c];
+    if (phase == 0) {
+        sc[BP_RZ * BP_MAXM + c] = s;
+        sc[BP_RZ0 * BP_MAXM + c] = s;
+        sc[BP_ACTIVE * BP_MAXM + c] = (s > 0.0) ? 1.0 : 0.0;
+        sc[BP_ALPHA * BP_MAXM + c] = 0.0;
+        sc[BP_BETA * BP_MAXM + c] = 0.0;
+    } else if (phase == 1) {
+        sc[BP_PQ * BP_MAXM + c] = s;
+        const bool act = sc[BP_ACTIVE * BP_MAXM + c] != 0.0 && s > 0.0;
+        if (!act) sc[BP_ACTIVE * BP_MAXM + c] = 0.0;
+        sc[BP_ALPHA * BP_MAXM + c] = act ? sc[BP_RZ * BP_MAXM + c] / s : 0.0;
+    } else {
+        const double rz = sc[BP_RZ * BP_MAXM + c];
+        bool act = sc[BP_ACTIVE * BP_MAXM + c] != 0.0;
+        if (act && !(s > tol2 * sc[BP_RZ0 * BP_MAXM + c])) act = false;   // converged (or NaN): freeze
+        sc[BP_BETA * BP_MAXM + c] = (act && rz > 0.0) ? s / rz : 0.0;
+        sc[BP_RZ * BP_MAXM + c] = s;
+        sc[BP_ACTIVE * BP_MAXM + c] = act ? 1.0 : 0.0;
+    }
+}
+
+// init: r = R (fixed dofs zeroed), z = T r, p = z, Z = 0
+template <int ND>
+__global__ void __launch_bounds__(256)
+bp_init_kernel(int64_t n_nodes, int m, const double* __restrict__ dinv, const uint8_t* __restrict__ fixed,
+               const double* __restrict__ R, int ldr, double* __restrict__ Z, double* __restrict__ r,
+               double* __restrict__ p, double* __restrict__ z) {
+    const int64_t total = n_nodes * m;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / m;
+        const int v = (int)(t - i * m);
+        const uint32_t fx = fixed ? fixed[i] : 0u;
+        double rv[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) rv[d] = ((fx >> d) & 1u) ? 0.0 : R[(i * ND + d) * ldr + v];
+        const double* B = dinv + i * ND * ND;
+#pragma unroll
+        for (int a = 0; a < ND; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < ND; ++b) s += __ldg(&B[a * ND + b]) * rv[b];
+            if ((fx >> a) & 1u) s = 0.0;
+            const int64_t o = (i * ND + a) * m + v;
+            Z[o] = 0.0; r[o] = rv[a]; z[o] = s; p[o] = s;
+        }
+    }
+}
+
+// Z += alpha p ; r -= alpha q ; z = T r
+template <int ND>
+__global__ void __launch_bounds__(256)
+bp_update_kernel(int64_t n_nodes, int m, const double* __restrict__ dinv, const uint8_t* __restrict__ fixed,
+                 const double* __restrict__ sc, const double* __restrict__ p, const double* __restrict__ q,
+                 double* __restrict__ Z, double* __restrict__ r, double* __restrict__ z) {
+    const int64_t total = n_nodes * m;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / m;
+        const int v = (int)(t - i * m);
+        const double alpha = sc[BP_ALPHA * BP_MAXM + v];
+        const uint32_t fx = fixed ? fixed[i] : 0u;
+        double rv[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const int64_t o = (i * ND + d) * m + v;
+            Z[o] += alpha * p[o];
+            rv[d] = r[o] - alpha * q[o];
+            if ((fx >> d) & 1u) rv[d] = 0.0;
+            r[o] = rv[d];
+        }
+        const double* B = dinv + i * ND * ND;
+#pragma unroll
+        for (int a = 0; a < ND; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < ND; ++b) s += __ldg(&B[a * ND + b]) * rv[b];
+            if ((fx >> a) & 1u) s = 0.0;
+            z[(i * ND + a) * m + v] = s;
+        }
+    }
+}
+
+// p = z + beta p   (final = 1: also W[:, :m] = Z)
+__global__ void __launch_bounds__(256)
+bp_direction_kernel(int64_t n, int m, const double* __restrict__ sc, const double* __restrict__ z, double* __restrict__ p) {
+    const int64_t total = n * m;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(t % m);
+        p[t] = z[t] + sc[BP_BETA * BP_MAXM + v] * p[t];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bp_store_kernel(int64_t n, int m, const double* __restrict__ Z, double* __restrict__ W, int ldw) {
+    const int64_t total = n * m;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / m;
+        W[r * ldw + (t - r * m)] = Z[t];
+    }
+}
+
+template <int ND>
+int block_pcg_run(femol_plan_t plan, const double* vals, const double* dinv, const uint8_t* fixed, const double* R, int ldr,
+                  double* W, int ldw, int m, int iters, double rel_tol, double* ws, cudaStream_t st) {
+    const int64_t n = plan->n_nodes * ND, nm = n * m;
+    double* Z = ws;
+    double* r = Z + nm;
+    double* p = r + nm;
+    double* q = p + nm;
+    double* z = q + nm;
+    double* partial = z + nm;                       // [BP_BLOCKS][m]
+    double* sc = partial + (int64_t)BP_BLOCKS * BP_MAXM;  // [BP_NS][BP_MAXM]
+    const int vgrid = femol_grid_for(plan->n_nodes * m, 256, plan->sm_count, 16);
+    int dgrid = (int)((n + 15) / 16);
+    if (dgrid > BP_BLOCKS) dgrid = BP_BLOCKS;
+    const double tol2 = rel_tol * rel_tol;
+    bp_init_kernel<ND><<<vgrid, 256, 0, st>>>(plan->n_nodes, m, dinv, fixed, R, ldr, Z, r, p, z);
+    FEMOL_LAUNCH_CHECK();
+    bp_dots_kernel<<<dgrid, 256, 0, st>>>(n, m, r, z, partial);
+    FEMOL_LAUNCH_CHECK();
+    bp_scalars_kernel<<<1, 32, 0, st>>>(dgrid, m, 0, tol2, partial, sc);
+    FEMOL_LAUNCH_CHECK();
+    for (int it = 0; it < iters; ++it) {
+        int rc = femol_spmm(plan, vals, p, m, q, m, m, st);
+        if (rc != FEMOL_OK) return rc;
+        bp_dots_kernel<<<dgrid, 256, 0, st>>>(n, m, p, q, partial);
+        FEMOL_LAUNCH_CHECK();
+        bp_scalars_kernel<<<1, 32, 0, st>>>(dgrid, m, 1, tol2, partial, sc);
+        FEMOL_LAUNCH_CHECK();
+        bp_update_kernel<ND><<<vgrid, 256, 0, st>>>(plan->n_nodes, m, dinv, fixed, sc, p, q, Z, r, z);
+        FEMOL_LAUNCH_CHECK();
+        bp_dots_kernel<<<dgrid, 256, 0, st>>>(n, m, r, z, partial);
+        FEMOL_LAUNCH_CHECK();
+        bp_scalars_kernel<<<1, 32, 0, st>>>(dgrid, m, 2, tol2, partial, sc);
+        FEMOL_LAUNCH_CHECK();
+        bp_direction_kernel<<<vgrid, 256, 0, st>>>(n, m, sc, z, p);
+        FEMOL_LAUNCH_CHECK();
+    }
+    bp_store_kernel<<<vgrid, 256, 0, st>>>(n, m, Z, W, ldw);
+    FEMOL_LAUNCH_CHECK();
+    return FEMOL_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t femol_block_pcg_workspace_doubles(femol_plan_t p, int m) {
+    if (!p) return 0;
+    return 5 * p->n_nodes * p->ndof * (int64_t)m + (int64_t)BP_BLOCKS * BP_MAXM + BP_NS * BP_MAXM;
+}
+
+extern "C" int femol_block_pcg(femol_plan_t p, const double* vals, const double* dinv, const uint8_t* fixed,
+                               const double* R, int ldr, double* W, int ldw, int m, int iters, double rel_tol,
+                               double* ws, void* stream) {
+    FEMOL_REQUIRE(p && vals && dinv && R && W && ws, "femol_block_pcg: null argument");
+    FEMOL_REQUIRE(m >= 1 && m <= BP_MAXM && iters >= 0 && rel_tol >= 0.0, "femol_block_pcg: bad block size / iteration count");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->ndof == 2) return block_pcg_run<2>(p, vals, dinv, fixed, R, ldr, W, ldw, m, iters, rel_tol, ws, st);
+    if (p->ndof == 6) return block_pcg_run<6>(p, vals, dinv, fixed, R, ldr, W, ldw, m, iters, rel_tol, ws, st);
+    femol_set_error("femol_block_pcg: unsupported ndof %d", p->ndof);
+    return FEMOL_E_ARG;
 }

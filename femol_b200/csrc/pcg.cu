@@ -206,9 +206,9 @@ int pcg_run(femol_plan_t plan, const double* vals, const double* f, double* u, d
     double h_sc[S_NSLOT];
     int total_iters = 0;
     int status = FEMOL_S_NOT_CONVERGED;
-    double true_rel = 0.0;
+    double true_rel = 0.0, prev_true_rel = 1e300;
     const int batch = 50;
-    for (int restart = 0; restart < 4; ++restart) {
+    for (int restart = 0; restart < 6; ++restart) {
         // (re)start from the true residual
         int rc = femol_spmv_launch(plan, vals, u, q, nullptr, nullptr, nullptr, st);
         if (rc != FEMOL_OK) return rc;
@@ -220,6 +220,10 @@ int pcg_run(femol_plan_t plan, const double* vals, const double* f, double* u, d
         true_rel = ff > 0.0 ? sqrt(h_sc[S_RR] / ff) : 0.0;
         if (h_sc[S_DONE] == 1.0 || ff == 0.0) { status = FEMOL_OK; break; }
         if (restart > 0 && true_rel <= 10.0 * rtol) { status = FEMOL_OK; break; }  // drift within a digit: accept
+        // the recurrence converged but the true residual no longer improves: attainable accuracy
+        // (~ eps * cond(A)) reached — a direct solver stops at the same level
+        if (restart > 1 && true_rel >= 0.5 * prev_true_rel) { status = FEMOL_S_STAGNATED; break; }
+        prev_true_rel = true_rel;
         if (total_iters >= max_iter) break;
 
         int parity = 0;
@@ -245,7 +249,7 @@ int pcg_run(femol_plan_t plan, const double* vals, const double* f, double* u, d
         if (!finished) break;  // out of iterations
         // converged on the recurrence: loop once more to verify against the true residual
     }
-    if (status != FEMOL_OK && status != FEMOL_S_BREAKDOWN) {
+    if (status == FEMOL_S_NOT_CONVERGED) {
         // report the true residual of whatever we have
         int rc = femol_spmv_launch(plan, vals, u, q, nullptr, nullptr, nullptr, st);
         if (rc != FEMOL_OK) return rc;

@@ -189,17 +189,27 @@ oc_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ dc, int 
     double* partC = ws + 2 * FEMOL_RED_MAX_BLOCKS;
     const int nblk = gridDim.x;
     const int64_t tid0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-    const double move = mode == 0 ? 0.5 : 0.3;
+    const bool vibe = (mode & 1) != 0, strict = (mode & 2) != 0;
+    const double move = vibe ? 0.3 : 0.5;
 
     // ---- phase 0: sign convention (COMP) / clamp + rescale (VIBE) ------------------------------
+    // TOM_SIMP.py:289-292 switches the sign convention of the WHOLE vector when any(dc > 0); the other
+    // sign then becomes NaN through the fractional power.  strict: exactly that.  Default: the sign of
+    // the entry of largest magnitude decides (identical whenever dc is one-signed, which is every case
+    // the reference survives) and entries of the opposite sign — rounding noise of u'Ku on elements in
+    // near rigid-body motion, ~1e-11 on a 4M-dof mesh — count as zero sensitivity instead of NaN.
     double sign = 1.0, scale = 1.0;
-    if (mode == 0) {
-        double anyp = 0.0;
-        for (int64_t e = tid0; e < n; e += nth) if (dc[e] > 0.0) anyp = 1.0;
-        const double bm = block_max(anyp, smem);
-        if (threadIdx.x == 0) __stcg(&partA[blockIdx.x], bm);
+    bool clamp_opposite = false;
+    if (!vibe) {
+        double mxp = 0.0, mxn = 0.0;
+        for (int64_t e = tid0; e < n; e += nth) { const double g = dc[e]; mxp = fmax(mxp, g); mxn = fmax(mxn, -g); }
+        const double bp = block_max(mxp, smem);
+        const double bn = block_max(mxn, smem);
+        if (threadIdx.x == 0) { __stcg(&partA[blockIdx.x], bp); __stcg(&partB[blockIdx.x], bn); }
         grid.sync();
-        sign = max_partials(partA, nblk, smem) > 0.0 ? 1.0 : -1.0;   // TOM_SIMP.py:289-292
+        const double gp = max_partials(partA, nblk, smem), gn = max_partials(partB, nblk, smem);
+        if (strict) sign = gp > 0.0 ? 1.0 : -1.0;
+        else { sign = gp > gn ? 1.0 : -1.0; clamp_opposite = true; }
     } else {
         double s[1] = {0.0}, mx = -INFINITY;
         for (int64_t e = tid0; e < n; e += nth) {
@@ -221,7 +231,11 @@ oc_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ dc, int 
     grid.sync();  // partA/partB are reused below
 
     // ---- phase 1: B_e = x_e * g_e^0.3 (stored in x_new) -----------------------------------------
-    for (int64_t e = tid0; e < n; e += nth) x_new[e] = x[e] * pow(sign * dc[e], 0.3);
+    for (int64_t e = tid0; e < n; e += nth) {
+        double g = sign * dc[e];
+        if (clamp_opposite && g < 0.0) g = 0.0;
+        x_new[e] = x[e] * pow(g, 0.3);
+    }
 
     // ---- phase 2: bisection on the Lagrange multiplier -----------------------------------------
     double l1 = 0.0, l2 = 100000.0, lmid = 0.0;
@@ -354,7 +368,7 @@ extern "C" int femol_filter_list(int64_t n_elem, const int32_t* nbr_ptr, const i
 extern "C" int femol_oc_update(int64_t n_elem, const double* x, double* dc, int mode, double volfrac, const double* areas,
                                const uint8_t* mask, double* x_new, double* scalars_out, double* ws, void* stream) {
     FEMOL_REQUIRE(x && dc && x_new && scalars_out && ws && n_elem > 0, "femol_oc_update: bad argument");
-    FEMOL_REQUIRE(mode == 0 || mode == 1, "femol_oc_update: mode must be 0 (COMP) or 1 (VIBE)");
+    FEMOL_REQUIRE(mode >= 0 && mode <= 2, "femol_oc_update: mode must be 0 (COMP), 1 (VIBE) or 2 (COMP, strict sign rule)");
     int per_sm = 0;
     FEMOL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oc_kernel, OC_THREADS, 0));
     FEMOL_REQUIRE(per_sm > 0, "femol_oc_update: kernel does not fit on an SM");

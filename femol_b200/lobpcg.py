@@ -106,12 +106,16 @@ def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False):
 class DeviceOps(object):
     """CUDA implementation of the block operations (csrc/lobpcg.cu through the C-ABI)."""
 
-    def __init__(self, plan, k_vals, m_vals, fixed_mask, m, precond_kind, X0):
+    def __init__(self, plan, k_vals, m_vals, fixed_mask, m, precond_kind, X0, inner_iters=0, inner_tol=1e-2):
+        """precond_kind: diagonal / block-diagonal inverse used directly (inner_iters = 0) or as the inner
+        preconditioner of `inner_iters` block-CG iterations on K (T ~ K^-1, femol_block_pcg)."""
         import torch
         from . import _lib
         self._lib, self._torch = _lib, torch
         self.plan, self.k_vals, self.m_vals, self.fixed = plan, k_vals, m_vals, fixed_mask
         self.m = m
+        self.inner_iters, self.inner_tol = int(inner_iters), float(inner_tol)
+        self._bp_ws = None
         n = X0.shape[0]
         self.n = n
         dev = X0.device
@@ -189,7 +193,16 @@ class DeviceOps(object):
 
     def precondition(self):
         L = self._lib
-        L.call('femol_precond_apply', self.plan, L.ptr(self.dinv), L.ptr(self.fixed) if self.fixed is not None else None,
+        fixed = L.ptr(self.fixed) if self.fixed is not None else None
+        if self.inner_iters > 0:
+            if self._bp_ws is None:
+                nd = int(L.load().femol_block_pcg_workspace_doubles(self.plan, self.m))
+                self._bp_ws = self._torch.empty(nd, dtype=self._torch.float64, device=self.k_vals.device)
+            L.call('femol_block_pcg', self.plan, L.ptr(self.k_vals), L.ptr(self.dinv), fixed, self._p('S', self.m),
+                   3 * self.m, self._p('S', self.m), 3 * self.m, self.m, self.inner_iters, self.inner_tol,
+                   L.ptr(self._bp_ws), L.stream())
+            return
+        L.call('femol_precond_apply', self.plan, L.ptr(self.dinv), fixed,
                self._p('S', self.m), 3 * self.m, self._p('S', self.m), 3 * self.m, self.m, L.stream())
 
     def vectors(self):

@@ -34,6 +34,7 @@ extern "C" {
 #define FEMOL_E_NOGPU (-4)    /* no CUDA device */
 #define FEMOL_S_NOT_CONVERGED 1
 #define FEMOL_S_BREAKDOWN 2   /* PCG/LOBPCG breakdown (p'Ap <= 0 or NaN) */
+#define FEMOL_S_STAGNATED 3   /* recurrence converged, true residual at its attainable floor (~eps*cond) */
 
 /* element types: reference FEMOL/elements.py classes T3 :43, T6 :277, Q4 :686, Q8 :1156 */
 #define FEMOL_T3 0
@@ -136,6 +137,14 @@ int femol_block_residual(int64_t n, int m, const double* KX, int ldk, const doub
 int femol_precond_setup(femol_plan_t plan, const double* vals, int kind, double* dinv, void* stream);
 int femol_precond_apply(femol_plan_t plan, const double* dinv, const uint8_t* fixed, const double* R, int ldr,
                         double* W, int ldw, int m, void* stream);
+/* W[:, :m] ~= K^-1 R[:, :m]: `iters` block-CG iterations (one recurrence per column on a shared SpMM,
+ * block-Jacobi preconditioned through dinv, fixed dofs kept at zero).  No host synchronisation: scalars stay
+ * on the device and a column freezes once its preconditioned residual dropped by rel_tol.  This is the
+ * "T ~ K^-1" preconditioner of LOBPCG.  W may alias R.  ws: femol_block_pcg_workspace_doubles(plan, m). */
+int64_t femol_block_pcg_workspace_doubles(femol_plan_t plan, int m);
+int femol_block_pcg(femol_plan_t plan, const double* vals, const double* dinv, const uint8_t* fixed,
+                    const double* R, int ldr, double* W, int ldw, int m, int iters, double rel_tol,
+                    double* ws, void* stream);
 
 /* ---- K7/K8: element sensitivities -----------------------------------------------------------
  * compliance (TOM_SIMP.py:126-226):  q_e = u_e' E_e u_e (and qc_e with Ecoat)
@@ -164,7 +173,11 @@ int femol_filter_list(int64_t n_elem, const int32_t* nbr_ptr, const int32_t* nbr
                       const double* x, const double* dc, double* out, void* stream);
 
 /* ---- K10: optimality-criteria update with device-side bisection ------------------------------
- * mode 0 = SIMP_COMP._get_new_x (TOM_SIMP.py:279-313): move 0.5, sign convention switched by any(dc>0)
+ * mode 0 = SIMP_COMP._get_new_x (TOM_SIMP.py:279-313): move 0.5; the sign convention follows the entry of
+ *          largest magnitude and entries of the opposite sign count as zero (identical to the reference for
+ *          one-signed dc; robust to rounding-level sign noise)
+ * mode 2 = as mode 0 with the reference's literal rule: any(dc>0) switches the sign of the whole vector and
+ *          the other sign becomes NaN (TOM_SIMP.py:289-297)
  * mode 1 = SIMP_VIBE._get_new_x (TOM.py:251-303): move 0.3, dl<0 -> 0, rescale by 1/max if sum(dl) < 1
  *          (dc is modified in place like the reference's self.dlmbd)
  * areas: NULL -> volume test by count (sum x - f N > 0), else area weighted (TOM.py:294).
