@@ -39,7 +39,7 @@ def parse():
     ap.add_argument('--nx', type=int, default=2000)
     ap.add_argument('--ny', type=int, default=1000)
     ap.add_argument('--rtol', type=float, default=1e-8)
-    ap.add_argument('--precond', default='block_jacobi')
+    ap.add_argument('--precond', default='auto')
     ap.add_argument('--sample-nx', type=int, default=400, help='CPU baseline sample mesh')
     ap.add_argument('--sample-ny', type=int, default=200)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -285,7 +285,7 @@ def run_gpu(args):
                 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': workload_name(args.nx, args.ny), 'ndof': n, 'nnz': nnz,
-                           'pcg': {'precond': args.precond, 'rtol': args.rtol, 'iterations_per_step': pcg_iters,
+                           'pcg': {'precond': problem.solver_info.get('preconditioner', args.precond), 'rtol': args.rtol, 'iterations_per_step': pcg_iters,
                                    'warm_start': True},
                            'l2_policy': 'inputs larger than L2 (CSR values %.0f MB per SpMV >> 126 MB L2)' % (8 * nnz / 1e6),
                            'parallelism': 'one independent design per GPU' if world > 1 else 'single GPU',

@@ -60,6 +60,7 @@ class _Device(object):
         self.nnz_node, self.nnz = int(info[0]), int(info[1])
         self.max_valence, self.max_row_nodes = int(info[2]), int(info[3])
         self.xpow = torch.empty(self.n_elem, dtype=torch.float64, device=self.dev)
+        self.xpow_m = torch.empty(self.n_elem, dtype=torch.float64, device=self.dev)
         self.red_ws = torch.zeros(int(_lib.load().femol_reduce_workspace_doubles()), dtype=torch.float64, device=self.dev)
         self._csr = None
         self._pcg_ws = None
@@ -124,7 +125,11 @@ class FEM_Problem(object):
         # solver controls (no reference counterpart: spsolve is direct)
         self.solver_rtol = 1e-10
         self.solver_max_iter = 200000
-        self.preconditioner = 'block_jacobi'
+        # 'auto': geometric multigrid on rectangle_Q4-ordered structured meshes, block-Jacobi otherwise;
+        # 'gmg' | 'block_jacobi' | 'jacobi' | 'none' force one
+        self.preconditioner = 'auto'
+        self.gmg_smoothing_steps = 2
+        self.gmg_omega = 0.6
         self.warm_start = True
         self.n_modes = 10
         self.modal_tol = 1e-8
@@ -145,6 +150,20 @@ class FEM_Problem(object):
         self._X_modal = None  # last eigenvector block (warm start)
         self._mask_key = None
         self._mask_dev = None
+        self._grid_shape = None
+        self._gmg = None
+        self._gmg_mask_key = None
+        self._gmg_stale = True
+        self._gmg_ws = None
+        self._K_scaled = False
+
+    def __del__(self):
+        try:
+            if getattr(self, '_gmg', None) is not None:
+                _lib.load().femol_gmg_destroy(self._gmg)
+                self._gmg = None
+        except Exception:
+            pass
 
     # ---- set-up (host) ----------------------------------------------------------------------------
     def define_materials(self, *materials):
@@ -264,9 +283,13 @@ class FEM_Problem(object):
         Ec, pe_c = self._element_matrices(which, True) if self.coating else (None, 0)
         x = self._x_device(X)
         vals = torch.empty(d.nnz, dtype=torch.float64, device=d.dev)
+        xpow = d.xpow if which == 'K' else d.xpow_m      # x^p of K is reused by the multigrid set-up
         _lib.call('femol_assemble', d.plan, _lib.ptr(Eb), pe_b, _lib.ptr(Ec), pe_c, _lib.ptr(x),
-                  float(expo) if expo is not None else 1.0, _lib.ptr(self._fixed_mask()), _lib.ptr(d.xpow),
+                  float(expo) if expo is not None else 1.0, _lib.ptr(self._fixed_mask()), _lib.ptr(xpow),
                   _lib.ptr(vals), _lib.stream())
+        if which == 'K':
+            self._K_scaled = x is not None
+            self._gmg_stale = True
         return vals
 
     # ---- assembly -----------------------------------------------------------------------------------
@@ -332,16 +355,73 @@ class FEM_Problem(object):
             self._U_dev = torch.zeros(d.n, dtype=torch.float64, device=d.dev)
         iters = ctypes.c_int(0)
         relres = ctypes.c_double(0.0)
-        rc = _lib.call('femol_pcg', d.plan, _lib.ptr(self._Kv), _lib.ptr(self._F_dev), _lib.ptr(self._U_dev),
-                       float(self.solver_rtol), int(self.solver_max_iter), _PRECOND[self.preconditioner],
-                       _lib.ptr(d.pcg_ws()), ctypes.byref(iters), ctypes.byref(relres), _lib.stream())
+        precond = self._effective_preconditioner()
+        if precond == 'gmg':
+            gmg = self._gmg_ready()
+            if self._gmg_ws is None:
+                self._gmg_ws = torch.empty(int(_lib.load().femol_pcg_gmg_workspace_doubles(d.plan)), dtype=torch.float64, device=d.dev)
+            rc = _lib.call('femol_pcg_gmg', d.plan, gmg, _lib.ptr(self._Kv), _lib.ptr(self._F_dev), _lib.ptr(self._U_dev),
+                           float(self.solver_rtol), int(self.solver_max_iter), _lib.ptr(self._gmg_ws),
+                           ctypes.byref(iters), ctypes.byref(relres), _lib.stream())
+        else:
+            rc = _lib.call('femol_pcg', d.plan, _lib.ptr(self._Kv), _lib.ptr(self._F_dev), _lib.ptr(self._U_dev),
+                           float(self.solver_rtol), int(self.solver_max_iter), _PRECOND[precond],
+                           _lib.ptr(d.pcg_ws()), ctypes.byref(iters), ctypes.byref(relres), _lib.stream())
         # status 0: converged to rtol; 3: recurrence converged and the TRUE residual sits at its attainable
         # floor (~ eps * cond(K), the level a direct solver reaches too); 1: iteration limit
         self.solver_info = {'iterations': iters.value, 'relres': relres.value, 'status': rc,
-                            'converged': rc in (0, _lib.S_STAGNATED)}
+                            'converged': rc in (0, _lib.S_STAGNATED), 'preconditioner': precond}
         if rc == _lib.S_BREAKDOWN:
             raise _lib.FemolError('PCG breakdown (matrix not positive definite?) after %d iterations' % iters.value)
         return self._U_dev
+
+    # ---- geometric multigrid (structured Q4 meshes) ---------------------------------------------------
+    def structured_grid_shape(self):
+        """(nx, ny) when the mesh is a rectangle_Q4-ordered structured quad grid (mesh.py:852-860), else None."""
+        if self._grid_shape is None:
+            shape = False
+            m = self.mesh
+            if m.structured and m.contains == ['quad'] and m.ElementClasses['quad'].N_nodes == 4:
+                nxp = int(np.count_nonzero(m.points[:, 1] == m.points[0, 1]))
+                nx = nxp - 1
+                if nx >= 1 and m.N_nodes % nxp == 0:
+                    ny = m.N_nodes // nxp - 1
+                    if ny >= 1 and nx * ny == m.N_ele:
+                        a = np.add.outer(np.arange(nx), nxp * np.arange(ny)).reshape(-1)
+                        exp = np.stack([a, a + 1, a + nx + 2, a + nx + 1], axis=1)
+                        if np.array_equal(np.asarray(m.cells['quad']), exp):
+                            shape = (nx, ny)
+            self._grid_shape = shape
+        return self._grid_shape or None
+
+    def _effective_preconditioner(self):
+        p = self.preconditioner
+        if p == 'auto':
+            shape = self.structured_grid_shape()
+            return 'gmg' if (shape and self.mesh.N_ele >= 64) else 'block_jacobi'
+        if p == 'gmg' and not self.structured_grid_shape():
+            raise _lib.FemolError("preconditioner='gmg' needs a rectangle_Q4-ordered structured mesh")
+        return p
+
+    def _gmg_ready(self):
+        """Create (once per Dirichlet set) and refresh (once per assembled K) the multigrid hierarchy."""
+        d = self.device
+        mask = self._fixed_mask()
+        if self._gmg is None or self._gmg_mask_key != self._mask_key:
+            if self._gmg is not None:
+                _lib.load().femol_gmg_destroy(self._gmg)
+            nx, ny = self.structured_grid_shape()
+            handle = ctypes.c_void_p()
+            _lib.call('femol_gmg_create', nx, ny, self.N_dof, d.plan, _lib.ptr(mask), int(self.gmg_smoothing_steps),
+                      float(self.gmg_omega), _lib.stream(), ctypes.byref(handle))
+            self._gmg, self._gmg_mask_key, self._gmg_stale = handle, self._mask_key, True
+        if self._gmg_stale:
+            Eb, _ = self._element_matrices('K', False)
+            Ec = self._element_matrices('K', True)[0] if self.coating else None
+            _lib.call('femol_gmg_setup', self._gmg, _lib.ptr(Eb), _lib.ptr(Ec),
+                      _lib.ptr(d.xpow) if self._K_scaled else None, _lib.ptr(self._Kv), _lib.stream())
+            self._gmg_stale = False
+        return self._gmg
 
     def _displacement_solve(self, verbose):
         """FEM.py:201-214"""
@@ -374,7 +454,8 @@ class FEM_Problem(object):
         if mask is not None:  # fixed dofs are projected out (the reference keeps them as lambda = 1 pairs)
             bits = (mask.to(torch.int32)[:, None] >> torch.arange(self.N_dof, device=d.dev, dtype=torch.int32)[None]) & 1
             X0[bits.reshape(-1).bool()] = 0.0
-        ops = _lobpcg.DeviceOps(d.plan, self._Kv, self._Mv, mask, m, _PRECOND[self.preconditioner], X0,
+        inner = self.preconditioner if self.preconditioner in ('none', 'jacobi', 'block_jacobi') else 'block_jacobi'
+        ops = _lobpcg.DeviceOps(d.plan, self._Kv, self._Mv, mask, m, _PRECOND[inner], X0,
                                 inner_iters=self.modal_inner_iters, inner_tol=self.modal_inner_tol)
         lam, rel, its = _lobpcg.lobpcg(ops, m, k, tol=self.modal_tol, max_iter=self.modal_max_iter)
         V = ops.vectors()

@@ -38,6 +38,13 @@ SIGNATURES = {
     'femol_spmv_csr': (c_int, [c_i64, P, P, P, P, P, P]),
     'femol_pcg_workspace_doubles': (c_i64, [P]),
     'femol_pcg': (c_int, [P, P, P, P, c_dbl, c_int, c_int, P, ctypes.POINTER(c_int), ctypes.POINTER(c_dbl), P]),
+    'femol_gmg_create': (c_int, [c_i64, c_i64, c_int, P, P, c_int, c_dbl, P, ctypes.POINTER(c_vp)]),
+    'femol_gmg_destroy': (c_int, [P]),
+    'femol_gmg_setup': (c_int, [P, P, P, P, P, P]),
+    'femol_gmg_info': (c_int, [P, ctypes.POINTER(c_i64)]),
+    'femol_gmg_apply': (c_int, [P, P, P, P]),
+    'femol_pcg_gmg_workspace_doubles': (c_i64, [P]),
+    'femol_pcg_gmg': (c_int, [P, P, P, P, P, c_dbl, c_int, P, ctypes.POINTER(c_int), ctypes.POINTER(c_dbl), P]),
     'femol_spmm': (c_int, [P, P, P, c_int, P, c_int, c_int, P]),
     'femol_gram_workspace_doubles': (c_i64, [c_int, c_int]),
     'femol_gram': (c_int, [c_i64, c_int, c_int, P, c_int, P, c_int, P, P, P]),

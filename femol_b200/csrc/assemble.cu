@@ -109,6 +109,178 @@ assemble_kernel(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, const int3
     }
 }
 
+// Main kernel: thread (node i, slot k) owns the ND x ND block of node pair (i, adj[i][k]) — no search and
+// no run-time division (SLOTS is a compile-time bound on the row length in nodes: 9 for structured Q4, so
+// interior rows use every lane).  The first ncu capture showed the item kernel above to be issue-bound
+// (451 M warp instructions, 16 % of DRAM peak; profiles/r01_*); this one also reads the contributing
+// (element, a, b) triples from the fixed-width ELL copy with one 16-byte load (W = 4 or 8 sources; W = 0:
+// pointer + list walk) and issues the x^p loads of all sources together.
+template <int ND, int NN, int W>
+struct BlockLoad {  // everything one node block needs from global memory, fetched before any use
+    int pb, len;
+    bool active;
+    uint32_t pk[W ? W : 1];
+    double w[W ? W : 1];
+    int32_t jn;
+    uint32_t fr, fc;
+};
+
+template <int ND, int NN, int W>
+__device__ __forceinline__ void load_phase1(BlockLoad<ND, NN, W>& L, int64_t i, int k, bool valid,
+                                            const int32_t* __restrict__ adj_ptr) {
+    L.pb = valid ? __ldg(&adj_ptr[i]) : 0;
+    L.len = valid ? __ldg(&adj_ptr[i + 1]) - L.pb : 0;
+    L.active = valid && k < L.len;
+}
+template <int ND, int NN, int W>
+__device__ __forceinline__ void load_phase2(BlockLoad<ND, NN, W>& L, int64_t i, int k, const int32_t* __restrict__ adj_idx,
+                                            const uint32_t* __restrict__ src_ell, const uint8_t* __restrict__ fixed) {
+    constexpr int WMAX = W ? W : 1;
+#pragma unroll
+    for (int q = 0; q < WMAX; ++q) L.pk[q] = 0xFFFFFFFFu;
+    L.jn = 0; L.fr = 0; L.fc = 0;
+    if (L.active) {
+        const int64_t pos = (int64_t)L.pb + k;
+        if (W) {
+#pragma unroll
+            for (int q = 0; q < WMAX / 4; ++q) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(src_ell + pos * WMAX) + q);
+                L.pk[4 * q] = v.x; L.pk[4 * q + 1] = v.y; L.pk[4 * q + 2] = v.z; L.pk[4 * q + 3] = v.w;
+            }
+        }
+        if (fixed) { L.jn = __ldg(&adj_idx[pos]); L.fr = fixed[i]; }
+    }
+}
+template <int ND, int NN, int W>
+__device__ __forceinline__ void load_phase3(BlockLoad<ND, NN, W>& L, const double* __restrict__ xpow,
+                                            const uint8_t* __restrict__ fixed) {
+    constexpr int WMAX = W ? W : 1;
+#pragma unroll
+    for (int q = 0; q < WMAX; ++q) L.w[q] = (L.pk[q] != 0xFFFFFFFFu && xpow) ? __ldg(&xpow[L.pk[q] >> 6]) : 1.0;
+    if (L.active && fixed) L.fc = fixed[L.jn];
+}
+
+template <int ND, int NN, int W>
+__device__ __forceinline__ void finish_block(const BlockLoad<ND, NN, W>& L, int64_t i, int k,
+                                             const int32_t* __restrict__ src_ptr, const uint32_t* __restrict__ src,
+                                             const double* __restrict__ e_base, int base_pe, const double* s_base,
+                                             const double* __restrict__ e_coat, int coat_pe, const double* s_coat,
+                                             const double* __restrict__ xpow, double* __restrict__ vals) {
+    constexpr int S = NN * ND;
+    constexpr int S2 = S * S;
+    constexpr int WMAX = W ? W : 1;
+    if (!L.active) return;
+    double acc[ND][ND];
+#pragma unroll
+    for (int a = 0; a < ND; ++a)
+#pragma unroll
+        for (int b = 0; b < ND; ++b) acc[a][b] = 0.0;
+
+    auto contribute = [&](uint32_t pk, double w) {
+        const int64_t e = pk >> 6;
+        const int off = (int)((pk >> 3) & 7) * ND * S + (int)(pk & 7) * ND;
+        const double* eb = base_pe ? e_base + e * S2 + off : s_base + off;
+        if (e_coat) {
+            const double* ec = coat_pe ? e_coat + e * S2 + off : s_coat + off;
+#pragma unroll
+            for (int a = 0; a < ND; ++a)
+#pragma unroll
+                for (int b = 0; b < ND; ++b) acc[a][b] += eb[a * S + b] + w * ec[a * S + b];
+        } else {
+#pragma unroll
+            for (int a = 0; a < ND; ++a)
+#pragma unroll
+                for (int b = 0; b < ND; ++b) acc[a][b] += w * eb[a * S + b];
+        }
+    };
+    if (W) {
+#pragma unroll
+        for (int q = 0; q < WMAX; ++q)
+            if (L.pk[q] != 0xFFFFFFFFu) contribute(L.pk[q], L.w[q]);
+    } else {
+        const int64_t pos = (int64_t)L.pb + k;
+        const int sb = __ldg(&src_ptr[pos]), se = __ldg(&src_ptr[pos + 1]);
+        for (int sidx = sb; sidx < se; ++sidx) {
+            const uint32_t pk = __ldg(&src[sidx]);
+            contribute(pk, xpow ? __ldg(&xpow[pk >> 6]) : 1.0);
+        }
+    }
+    if (L.fr | L.fc) {  // FEM.py:902-930: fixed rows and columns zeroed, unit diagonal
+        const bool diag = L.jn == (int32_t)i;
+#pragma unroll
+        for (int a = 0; a < ND; ++a)
+#pragma unroll
+            for (int b = 0; b < ND; ++b)
+                if (((L.fr >> a) | (L.fc >> b)) & 1u) acc[a][b] = (diag && a == b) ? 1.0 : 0.0;
+    }
+    double* o = vals + (int64_t)ND * ND * L.pb + (int64_t)k * ND;
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+        double2* o2 = reinterpret_cast<double2*>(o + (int64_t)a * L.len * ND);
+#pragma unroll
+        for (int b = 0; b < ND; b += 2) __stcs(&o2[b >> 1], make_double2(acc[a][b], acc[a][b + 1]));
+    }
+}
+
+template <int ND, int NN, int SLOTS, int W>
+__global__ void __launch_bounds__(256, ND == 2 ? 4 : 2)
+assemble_slots_kernel(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx,
+                      const int32_t* __restrict__ src_ptr, const uint32_t* __restrict__ src,
+                      const uint32_t* __restrict__ src_ell,
+                      const double* __restrict__ e_base, int base_pe, const double* __restrict__ e_coat, int coat_pe,
+                      const double* __restrict__ xpow, const uint8_t* __restrict__ fixed, double* __restrict__ vals) {
+    constexpr int S2 = NN * ND * NN * ND;
+    constexpr int NPB = 256 / SLOTS;  // nodes per block pass
+    constexpr int ILP = ND == 2 ? 2 : 1;  // node blocks in flight per thread
+    extern __shared__ double s_mat[];
+    double* s_base = s_mat;
+    double* s_coat = s_mat + (base_pe ? 0 : S2);
+    if (!base_pe)
+        for (int i = threadIdx.x; i < S2; i += blockDim.x) s_base[i] = e_base[i];
+    if (e_coat && !coat_pe)
+        for (int i = threadIdx.x; i < S2; i += blockDim.x) s_coat[i] = e_coat[i];
+    __syncthreads();
+    const int ln = threadIdx.x / SLOTS, k = threadIdx.x - ln * SLOTS;
+    if (ln >= NPB) return;
+    const int64_t step = (int64_t)gridDim.x * NPB;
+    for (int64_t i0 = (int64_t)blockIdx.x * NPB + ln; i0 < n_nodes; i0 += ILP * step) {
+        BlockLoad<ND, NN, W> L[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) load_phase1(L[u], i0 + u * step, k, i0 + u * step < n_nodes, adj_ptr);
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) load_phase2(L[u], i0 + u * step, k, adj_idx, src_ell, fixed);
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) load_phase3(L[u], xpow, fixed);
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+            finish_block<ND, NN, W>(L[u], i0 + u * step, k, src_ptr, src, e_base, base_pe, s_base, e_coat, coat_pe, s_coat,
+                                    xpow, vals);
+    }
+}
+
+template <int ND, int NN, int SLOTS, int W>
+int launch_slots_w(femol_plan_t p, const double* e_base, int base_pe, const double* e_coat, int coat_pe,
+                   const double* xpow, const uint8_t* fixed, double* vals, size_t smem, cudaStream_t st) {
+    auto kern = assemble_slots_kernel<ND, NN, SLOTS, W>;
+    if (smem > 48 * 1024) FEMOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr int NPB = 256 / SLOTS;
+    int64_t grid = (p->n_nodes + NPB - 1) / NPB;
+    const int64_t cap = (int64_t)p->sm_count * 32;
+    if (grid > cap) grid = cap;
+    kern<<<(int)grid, 256, smem, st>>>(p->n_nodes, p->adj_ptr, p->adj_idx, p->src_ptr, p->src, p->src_ell, e_base, base_pe,
+                                       e_coat, coat_pe, xpow, fixed, vals);
+    FEMOL_LAUNCH_CHECK();
+    return FEMOL_OK;
+}
+
+template <int ND, int NN, int SLOTS>
+int launch_slots(femol_plan_t p, const double* e_base, int base_pe, const double* e_coat, int coat_pe,
+                 const double* xpow, const uint8_t* fixed, double* vals, size_t smem, cudaStream_t st) {
+    if (p->ell_width == 4) return launch_slots_w<ND, NN, SLOTS, 4>(p, e_base, base_pe, e_coat, coat_pe, xpow, fixed, vals, smem, st);
+    if (p->ell_width == 8) return launch_slots_w<ND, NN, SLOTS, 8>(p, e_base, base_pe, e_coat, coat_pe, xpow, fixed, vals, smem, st);
+    return launch_slots_w<ND, NN, SLOTS, 0>(p, e_base, base_pe, e_coat, coat_pe, xpow, fixed, vals, smem, st);
+}
+
 template <int ND, int NN>
 int launch_assemble(femol_plan_t p, const double* e_base, int base_pe, const double* e_coat, int coat_pe,
                     const double* xpow, const uint8_t* fixed, double* vals, cudaStream_t st) {
@@ -116,6 +288,12 @@ int launch_assemble(femol_plan_t p, const double* e_base, int base_pe, const dou
     size_t smem = 0;
     if (!base_pe) smem += S2 * sizeof(double);
     if (e_coat && !coat_pe) smem += S2 * sizeof(double);
+    const int mr = p->max_row_nodes;
+#define SLOT_CASE(SL) \
+    if (mr <= SL) return launch_slots<ND, NN, SL>(p, e_base, base_pe, e_coat, coat_pe, xpow, fixed, vals, smem, st);
+    SLOT_CASE(7) SLOT_CASE(9) SLOT_CASE(13) SLOT_CASE(19) SLOT_CASE(21) SLOT_CASE(32)
+#undef SLOT_CASE
+    // very irregular meshes (a node with more than 32 neighbours): generic item kernel
     auto kern = assemble_kernel<ND, NN>;
     if (smem > 48 * 1024) FEMOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (p->n_nodes + ASM_NODES - 1) / ASM_NODES;

@@ -47,6 +47,8 @@ struct femol_plan {
     int32_t* adj_idx;   // [nnz_node (+pad)] sorted per node
     int32_t* src_ptr;   // [nnz_node+1] contributions of each node block (transposed scatter map)
     uint32_t* src;      // [n_elem*nn*nn] packed (elem << 6 | local row node << 3 | local col node), ascending
+    uint32_t* src_ell;  // [nnz_node][ell_width] the same lists at fixed width (0xFFFFFFFF = empty), or NULL
+    int ell_width;      // 4, 8 or 0 (a node pair with more than 8 contributing elements: lists only)
     int sm_count;
 };
 

@@ -1,0 +1,508 @@
+// Geometric multigrid preconditioner for structured Q4 meshes (plane stress and Reissner-Mindlin plate).
+//
+// Why: Jacobi / block-Jacobi PCG needs ~10^4 iterations on the 4 M-dof SIMP cantilever (profiles/r01): the
+// iteration count, not the kernel bandwidth, decides SIMP iterations/s (SURVEY §7 "hard parts").  A V-cycle
+// costs ~7 SpMV-equivalents and brings the count to O(10^1-10^2).
+//
+// Hierarchy: level l+1 has ceil(n/2) elements per direction (any n: a trailing coarse element may cover a
+// single fine element); nodes are numbered x-fastest and elements e = i*ny + j on every level (the reference's
+// meshzoo ordering, mesh.py:852-860), so every level reuses femol_plan_create / femol_assemble / the node-block
+// SpMV unchanged.  Coarse operators are Galerkin, formed ELEMENT-WISE:
+//      K_c = P^T K P = sum_E sum_{children c of E} P_c^T (x_c^p Ke) P_c ,
+// i.e. one S x S matrix per coarse element (bilinear interpolation weights 0, 1/2, 1), then an ordinary
+// per-element assembly.  Dirichlet dofs: fine fixed dofs neither interpolate nor restrict (their rows/columns
+// are masked in the child matrices); a coarse node that coincides with a fixed fine node is fixed.
+// Smoother: damped block-Jacobi (ndof x ndof node blocks), nu pre + nu post sweeps -> symmetric V-cycle, valid
+// as a CG preconditioner.  Coarsest level: dense inverse computed on the device by one CTA.
+#include <math.h>
+#include <string.h>
+#include "common.cuh"
+#include "spmv.cuh"
+
+extern "C" int femol_precond_setup(femol_plan_t p, const double* vals, int kind, double* dinv, void* stream);
+
+namespace {
+
+constexpr int GMG_MAX_LEVELS = 20;
+constexpr int GMG_COARSE_MAX_DOF = 320;
+
+struct Level {
+    int64_t nx, ny, n_nodes, n_elem, n;
+    femol_plan* plan;   // level 0: borrowed
+    uint8_t* fixed;     // node masks (level 0: borrowed, may be NULL)
+    double* ke;         // [n_elem][S][S] (levels >= 1)
+    double* vals;       // CSR values (levels >= 1; level 0: set per setup)
+    double* dinv;       // [n_nodes][ND][ND]
+    double *r, *e, *t;  // work vectors (level 0: r, e supplied by the caller through vcycle)
+};
+
+}  // namespace
+
+struct femol_gmg {
+    int nd, n_levels, nu;
+    double omega;
+    Level lv[GMG_MAX_LEVELS];
+    double* coarse_inv;  // dense inverse of the coarsest operator [nc][nc]
+    int64_t nc;
+};
+
+namespace {
+
+// ---- structured-grid helpers ------------------------------------------------------------------------------
+__host__ __device__ inline int64_t coarse_of(int64_t n) { return (n + 1) / 2; }
+
+// 1-D interpolation: fine node i (0..n) -> coarse nodes I0 (weight w0) and I1 (weight w1, may be 0)
+__device__ __forceinline__ void cmap1d(int64_t i, int64_t n, int64_t& I0, double& w0, int64_t& I1, double& w1) {
+    if ((i & 1) == 0) { I0 = i >> 1; w0 = 1.0; I1 = I0; w1 = 0.0; }
+    else if (i == n) { I0 = (i + 1) >> 1; w0 = 1.0; I1 = I0; w1 = 0.0; }   // odd n: last fine node is a coarse node
+    else { I0 = i >> 1; w0 = 0.5; I1 = I0 + 1; w1 = 0.5; }
+}
+
+__global__ void make_conn(int64_t nx, int64_t ny, int32_t* __restrict__ conn) {
+    const int64_t ne = nx * ny;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / ny, j = e - i * ny;
+        const int64_t a = i + (nx + 1) * j;
+        conn[4 * e + 0] = (int32_t)a; conn[4 * e + 1] = (int32_t)(a + 1);
+        conn[4 * e + 2] = (int32_t)(a + nx + 2); conn[4 * e + 3] = (int32_t)(a + nx + 1);
+    }
+}
+
+__global__ void coarsen_mask(int64_t nxf, int64_t nyf, const uint8_t* __restrict__ ff, int64_t nxc, int64_t nyc,
+                             uint8_t* __restrict__ fc) {
+    const int64_t nn = (nxc + 1) * (nyc + 1);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nn; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t J = t / (nxc + 1), I = t - J * (nxc + 1);
+        const int64_t i = min(2 * I, nxf), j = min(2 * J, nyf);
+        fc[t] = ff ? ff[j * (nxf + 1) + i] : 0;
+    }
+}
+
+// ---- element-wise Galerkin coarsening ----------------------------------------------------------------------
+// One warp per coarse element.  LEVEL0: child matrices are x_c^p * Ke (+ coat) from the shared element matrix;
+// otherwise they are the previous level's per-element matrices.
+template <int ND, bool LEVEL0>
+__global__ void __launch_bounds__(128)
+coarsen_elements(int64_t nxf, int64_t nyf, int64_t nxc, int64_t nyc, const double* __restrict__ child_ke,
+                 const double* __restrict__ e_base, const double* __restrict__ e_coat, const double* __restrict__ xpow,
+                 const uint8_t* __restrict__ fixed_f, double* __restrict__ out) {
+    constexpr int S = 4 * ND, S2 = S * S;
+    __shared__ double s_child[4][S2];  // one warp's child matrix at a time
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t nec = nxc * nyc;
+    const int64_t warp0 = (int64_t)blockIdx.x * 4 + wid, nwarps = (int64_t)gridDim.x * 4;
+    constexpr int NE = (S2 + 31) / 32;
+    for (int64_t E = warp0; E < nec; E += nwarps) {
+        const int64_t I = E / nyc, J = E - I * nyc;
+        const bool fullx = 2 * I + 1 < nxf, fully = 2 * J + 1 < nyf;
+        double acc[NE];
+#pragma unroll
+        for (int m = 0; m < NE; ++m) acc[m] = 0.0;
+        for (int ca = 0; ca <= (fullx ? 1 : 0); ++ca)
+            for (int cb = 0; cb <= (fully ? 1 : 0); ++cb) {
+                const int64_t ci = 2 * I + ca, cj = 2 * J + cb;
+                const int64_t c = ci * nyf + cj;  // fine element id
+                // fine node ids of the child (Q4 order) for the fixed mask
+                const int64_t n00 = ci + (nxf + 1) * cj;
+                const int64_t cn[4] = {n00, n00 + 1, n00 + nxf + 2, n00 + nxf + 1};
+                uint32_t fm[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) fm[q] = fixed_f ? fixed_f[cn[q]] : 0u;
+                __syncwarp();
+                const double w = (LEVEL0 && xpow) ? xpow[c] : 1.0;
+                for (int idx = lane; idx < S2; idx += 32) {
+                    const int r = idx / S, cc = idx - r * S;
+                    double v;
+                    if (LEVEL0) v = e_coat ? e_base[idx] + w * e_coat[idx] : w * e_base[idx];
+                    else v = child_ke[c * S2 + idx];
+                    if (((fm[r / ND] >> (r % ND)) | (fm[cc / ND] >> (cc % ND))) & 1u) v = 0.0;
+                    s_child[wid][idx] = v;
+                }
+                __syncwarp();
+                // parametric position of the child's local nodes inside the parent: (s, t) in {0, 1/2, 1}
+                const double s0 = fullx ? 0.5 * ca : 0.0, s1 = fullx ? 0.5 * (ca + 1) : 1.0;
+                const double t0 = fully ? 0.5 * cb : 0.0, t1 = fully ? 0.5 * (cb + 1) : 1.0;
+                const double ps[4] = {s0, s1, s1, s0}, pt[4] = {t0, t0, t1, t1};
+                double W[4][4];  // W[child node][parent node]
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    W[q][0] = (1 - ps[q]) * (1 - pt[q]); W[q][1] = ps[q] * (1 - pt[q]);
+                    W[q][2] = ps[q] * pt[q]; W[q][3] = (1 - ps[q]) * pt[q];
+                }
+#pragma unroll
+                for (int m = 0; m < NE; ++m) {
+                    const int idx = lane + 32 * m;
+                    if (idx < S2) {
+                        const int r = idx / S, cc = idx - r * S;
+                        const int p = r / ND, da = r - p * ND, q = cc / ND, db = cc - q * ND;
+                        double v = 0.0;
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            const double wa = W[a][p];
+                            if (wa != 0.0) {
+#pragma unroll
+                                for (int b = 0; b < 4; ++b) v += wa * W[b][q] * s_child[wid][(a * ND + da) * S + b * ND + db];
+                            }
+                        }
+                        acc[m] += v;
+                    }
+                }
+            }
+        double* o = out + E * S2;
+#pragma unroll
+        for (int m = 0; m < NE; ++m) {
+            const int idx = lane + 32 * m;
+            if (idx < S2) o[idx] = acc[m];
+        }
+    }
+}
+
+// ---- transfer operators ---------------------------------------------------------------------------------------
+// r_c = P^T r_f   (fine fixed dofs do not restrict; coarse fixed dofs receive 0)
+template <int ND>
+__global__ void __launch_bounds__(256)
+restrict_kernel(int64_t nxf, int64_t nyf, int64_t nxc, int64_t nyc, const uint8_t* __restrict__ ff,
+                const uint8_t* __restrict__ fc, const double* __restrict__ rf, double* __restrict__ rc) {
+    const int64_t nn = (nxc + 1) * (nyc + 1);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nn; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t J = t / (nxc + 1), I = t - J * (nxc + 1);
+        const int64_t ic = min(2 * I, nxf), jc = min(2 * J, nyf);
+        double acc[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) acc[d] = 0.0;
+        for (int dj = -1; dj <= 1; ++dj) {
+            const int64_t j = jc + dj;
+            if (j < 0 || j > nyf) continue;
+            int64_t J0, J1; double v0, v1;
+            cmap1d(j, nyf, J0, v0, J1, v1);
+            const double wy = (J0 == J ? v0 : 0.0) + (J1 == J && v1 != 0.0 ? v1 : 0.0);
+            if (wy == 0.0) continue;
+            for (int di = -1; di <= 1; ++di) {
+                const int64_t i = ic + di;
+                if (i < 0 || i > nxf) continue;
+                int64_t I0, I1; double u0, u1;
+                cmap1d(i, nxf, I0, u0, I1, u1);
+                const double wx = (I0 == I ? u0 : 0.0) + (I1 == I && u1 != 0.0 ? u1 : 0.0);
+                if (wx == 0.0) continue;
+                const int64_t nf = j * (nxf + 1) + i;
+                const uint32_t fm = ff ? ff[nf] : 0u;
+                const double w = wx * wy;
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                    if (!((fm >> d) & 1u)) acc[d] += w * rf[nf * ND + d];
+            }
+        }
+        const uint32_t cm = fc ? fc[t] : 0u;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) rc[t * ND + d] = ((cm >> d) & 1u) ? 0.0 : acc[d];
+    }
+}
+
+// e_f += P e_c   (fixed fine dofs untouched)
+template <int ND>
+__global__ void __launch_bounds__(256)
+prolong_add_kernel(int64_t nxf, int64_t nyf, int64_t nxc, const uint8_t* __restrict__ ff,
+                   const double* __restrict__ ec, double* __restrict__ ef) {
+    const int64_t nn = (nxf + 1) * (nyf + 1);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nn; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = t / (nxf + 1), i = t - j * (nxf + 1);
+        int64_t I0, I1, J0, J1; double u0, u1, v0, v1;
+        cmap1d(i, nxf, I0, u0, I1, u1);
+        cmap1d(j, nyf, J0, v0, J1, v1);
+        const uint32_t fm = ff ? ff[t] : 0u;
+        const int64_t c00 = J0 * (nxc + 1) + I0, c10 = J0 * (nxc + 1) + I1, c01 = J1 * (nxc + 1) + I0, c11 = J1 * (nxc + 1) + I1;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            if ((fm >> d) & 1u) continue;
+            double v = u0 * v0 * ec[c00 * ND + d];
+            if (u1 != 0.0) v += u1 * v0 * ec[c10 * ND + d];
+            if (v1 != 0.0) { v += u0 * v1 * ec[c01 * ND + d]; if (u1 != 0.0) v += u1 * v1 * ec[c11 * ND + d]; }
+            ef[t * ND + d] += v;
+        }
+    }
+}
+
+// ---- smoother ------------------------------------------------------------------------------------------------------
+// FIRST: e = omega Dinv r ; else e += omega Dinv (r - Ke)
+template <int ND, bool FIRST>
+__global__ void __launch_bounds__(256)
+jacobi_kernel(int64_t n_nodes, double omega, const double* __restrict__ dinv, const double* __restrict__ r,
+              const double* __restrict__ Ke, double* __restrict__ e) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+        double d[ND];
+#pragma unroll
+        for (int a = 0; a < ND; ++a) d[a] = FIRST ? r[i * ND + a] : r[i * ND + a] - Ke[i * ND + a];
+        const double* B = dinv + i * ND * ND;
+#pragma unroll
+        for (int a = 0; a < ND; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < ND; ++b) s += __ldg(&B[a * ND + b]) * d[b];
+            if (FIRST) e[i * ND + a] = omega * s; else e[i * ND + a] += omega * s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+residual_kernel(int64_t n, const double* __restrict__ r, const double* __restrict__ Ke, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = r[i] - Ke[i];
+}
+
+// ---- coarsest level: dense inverse by Gauss-Jordan in one CTA ----------------------------------------------------
+__global__ void csr_to_dense(int64_t n, const int32_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx, int nd,
+                             const double* __restrict__ vals, double* __restrict__ A) {
+    const int64_t n_nodes = n / nd;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = r / nd;
+        const int da = (int)(r - i * nd);
+        const int pb = adj_ptr[i], len = adj_ptr[i + 1] - pb;
+        const double* a = vals + (int64_t)nd * nd * pb + (int64_t)da * len * nd;
+        for (int k = 0; k < len; ++k)
+            for (int db = 0; db < nd; ++db) A[r * n + (int64_t)adj_idx[pb + k] * nd + db] = a[k * nd + db];
+    }
+    (void)n_nodes;
+}
+
+// In-place Gauss-Jordan inversion of the SPD matrix A (n x n) without pivoting; a non-positive pivot (a coarse
+// dof that lost all its stiffness) is replaced by an identity row/column.
+__global__ void __launch_bounds__(1024)
+dense_inverse(int n, double* __restrict__ A) {
+    __shared__ double s_piv;
+    __shared__ double s_scale;
+    if (threadIdx.x == 0) {
+        double mx = 0.0;
+        for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(A[(int64_t)i * n + i]));
+        s_scale = mx;
+    }
+    __syncthreads();
+    const double tiny = 1e-13 * s_scale;
+    for (int k = 0; k < n; ++k) {
+        if (threadIdx.x == 0) s_piv = A[(int64_t)k * n + k];
+        __syncthreads();
+        double piv = s_piv;
+        const bool dead = !(piv > tiny);
+        if (dead) {  // decouple dof k
+            for (int j = threadIdx.x; j < n; j += blockDim.x) { A[(int64_t)k * n + j] = 0.0; A[(int64_t)j * n + k] = 0.0; }
+            __syncthreads();
+            if (threadIdx.x == 0) A[(int64_t)k * n + k] = 0.0;
+            __syncthreads();
+            continue;
+        }
+        const double ip = 1.0 / piv;
+        // row k scaled (pivot element becomes 1/piv)
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            const int64_t o = (int64_t)k * n + j;
+            A[o] = (j == k) ? ip : A[o] * ip;
+        }
+        __syncthreads();
+        // eliminate column k from every other row
+        for (int64_t t = threadIdx.x; t < (int64_t)n * n; t += blockDim.x) {
+            const int i = (int)(t / n), j = (int)(t - (int64_t)i * n);
+            if (i == k || j == k) continue;
+            A[t] -= A[(int64_t)i * n + k] * A[(int64_t)k * n + j];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            if (i != k) A[(int64_t)i * n + k] = -A[(int64_t)i * n + k] * ip;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dense_apply(int n, const double* __restrict__ Ainv, const double* __restrict__ r, double* __restrict__ e) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        double s = 0.0;
+        for (int j = lane; j < n; j += 32) s += Ainv[(int64_t)i * n + j] * r[j];
+        s = warp_sum(s);
+        if (lane == 0) e[i] = s;
+    }
+}
+
+int grid_for(int64_t n, int block = 256) {
+    int64_t g = (n + block - 1) / block;
+    const int64_t cap = (int64_t)femol_sm_count() * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+template <int ND>
+int smooth(femol_gmg* g, int l, const double* r, double* e, bool zero_start, cudaStream_t st) {
+    Level& L = g->lv[l];
+    const int grid = grid_for(L.n_nodes);
+    for (int s = 0; s < g->nu; ++s) {
+        if (s == 0 && zero_start) {
+            jacobi_kernel<ND, true><<<grid, 256, 0, st>>>(L.n_nodes, g->omega, L.dinv, r, nullptr, e);
+            FEMOL_LAUNCH_CHECK();
+        } else {
+            int rc = femol_spmv_launch(L.plan, L.vals, e, L.t, nullptr, nullptr, nullptr, st);
+            if (rc != FEMOL_OK) return rc;
+            jacobi_kernel<ND, false><<<grid, 256, 0, st>>>(L.n_nodes, g->omega, L.dinv, r, L.t, e);
+            FEMOL_LAUNCH_CHECK();
+        }
+    }
+    return FEMOL_OK;
+}
+
+template <int ND>
+int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st) {
+    Level& L = g->lv[l];
+    if (l == g->n_levels - 1) {
+        dense_apply<<<grid_for((int64_t)L.n * 32), 256, 0, st>>>((int)L.n, g->coarse_inv, r, e);
+        FEMOL_LAUNCH_CHECK();
+        return FEMOL_OK;
+    }
+    Level& C = g->lv[l + 1];
+    int rc = smooth<ND>(g, l, r, e, true, st);
+    if (rc != FEMOL_OK) return rc;
+    rc = femol_spmv_launch(L.plan, L.vals, e, L.t, nullptr, nullptr, nullptr, st);
+    if (rc != FEMOL_OK) return rc;
+    residual_kernel<<<grid_for(L.n), 256, 0, st>>>(L.n, r, L.t, L.t);
+    FEMOL_LAUNCH_CHECK();
+    restrict_kernel<ND><<<grid_for(C.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, C.ny, L.fixed, C.fixed, L.t, C.r);
+    FEMOL_LAUNCH_CHECK();
+    rc = vcycle<ND>(g, l + 1, C.r, C.e, st);
+    if (rc != FEMOL_OK) return rc;
+    prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e);
+    FEMOL_LAUNCH_CHECK();
+    return smooth<ND>(g, l, r, e, false, st);
+}
+
+}  // namespace
+
+int femol_gmg_vcycle_internal(femol_gmg* g, const double* r, double* z, cudaStream_t st) {
+    return g->nd == 2 ? vcycle<2>(g, 0, r, z, st) : vcycle<6>(g, 0, r, z, st);
+}
+
+extern "C" int femol_gmg_destroy(femol_gmg* g) {
+    if (!g) return FEMOL_OK;
+    for (int l = 0; l < g->n_levels; ++l) {
+        Level& L = g->lv[l];
+        if (l > 0) {
+            femol_plan_destroy(L.plan);
+            cudaFree(L.fixed); cudaFree(L.ke); cudaFree(L.vals); cudaFree(L.r); cudaFree(L.e);
+        }
+        cudaFree(L.dinv); cudaFree(L.t);
+    }
+    cudaFree(g->coarse_inv);
+    delete g;
+    return FEMOL_OK;
+}
+
+extern "C" int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t fine_plan, const uint8_t* fine_fixed,
+                                int nu, double omega, void* stream, femol_gmg** out) {
+    FEMOL_REQUIRE(out && fine_plan && nx >= 1 && ny >= 1, "femol_gmg_create: bad argument");
+    FEMOL_REQUIRE(ndof == 2 || ndof == 6, "femol_gmg_create: ndof must be 2 or 6");
+    FEMOL_REQUIRE(fine_plan->nn == 4 && fine_plan->ndof == ndof && fine_plan->n_elem == nx * ny &&
+                  fine_plan->n_nodes == (nx + 1) * (ny + 1), "femol_gmg_create: plan is not an nx x ny structured Q4 mesh");
+    cudaStream_t st = (cudaStream_t)stream;
+    femol_gmg* g = new femol_gmg();
+    memset(g, 0, sizeof(*g));
+    g->nd = ndof; g->nu = nu > 0 ? nu : 2; g->omega = omega > 0 ? omega : 0.6;
+    auto fail = [&](int code) { femol_gmg_destroy(g); return code; };
+#define GCHECK(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            femol_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return fail(FEMOL_E_CUDA);                                                            \
+        }                                                                                         \
+    } while (0)
+    int l = 0;
+    int64_t cx = nx, cy = ny;
+    const int S2 = 16 * ndof * ndof;
+    while (true) {
+        Level& L = g->lv[l];
+        L.nx = cx; L.ny = cy; L.n_nodes = (cx + 1) * (cy + 1); L.n_elem = cx * cy; L.n = L.n_nodes * ndof;
+        g->n_levels = l + 1;
+        GCHECK(cudaMalloc(&L.dinv, L.n_nodes * ndof * ndof * sizeof(double)));
+        GCHECK(cudaMalloc(&L.t, L.n * sizeof(double)));
+        if (l == 0) {
+            L.plan = fine_plan;
+            L.fixed = const_cast<uint8_t*>(fine_fixed);
+        } else {
+            Level& F = g->lv[l - 1];
+            int32_t* conn = nullptr;
+            GCHECK(cudaMalloc(&conn, L.n_elem * 4 * sizeof(int32_t)));
+            make_conn<<<grid_for(L.n_elem), 256, 0, st>>>(cx, cy, conn);
+            int rc = femol_plan_create(L.n_elem, 4, ndof, L.n_nodes, conn, st, &L.plan);
+            cudaFree(conn);
+            if (rc != FEMOL_OK) return fail(rc);
+            GCHECK(cudaMalloc(&L.fixed, L.n_nodes));
+            coarsen_mask<<<grid_for(L.n_nodes), 256, 0, st>>>(F.nx, F.ny, F.fixed, cx, cy, L.fixed);
+            GCHECK(cudaGetLastError());
+            GCHECK(cudaMalloc(&L.ke, L.n_elem * S2 * sizeof(double)));
+            GCHECK(cudaMalloc(&L.vals, L.plan->nnz * sizeof(double)));
+            GCHECK(cudaMalloc(&L.r, L.n * sizeof(double)));
+            GCHECK(cudaMalloc(&L.e, L.n * sizeof(double)));
+        }
+        const bool small = L.n <= GMG_COARSE_MAX_DOF && l > 0;
+        if (small || (cx == 1 && cy == 1) || l == GMG_MAX_LEVELS - 1) break;
+        cx = coarse_of(cx); cy = coarse_of(cy);
+        ++l;
+    }
+    Level& CL = g->lv[g->n_levels - 1];
+    if (g->n_levels < 2 || CL.n > 4096) {
+        femol_set_error("femol_gmg_create: mesh too small (%d levels) or coarsest level too large (%lld dofs)", g->n_levels, (long long)CL.n);
+        return fail(FEMOL_E_ARG);
+    }
+    g->nc = CL.n;
+    GCHECK(cudaMalloc(&g->coarse_inv, CL.n * CL.n * sizeof(double)));
+    GCHECK(cudaStreamSynchronize(st));
+#undef GCHECK
+    *out = g;
+    return FEMOL_OK;
+}
+
+// (Re)build the hierarchy for the current densities: called once per assembled fine matrix.
+extern "C" int femol_gmg_setup(femol_gmg* g, const double* e_base, const double* e_coat, const double* xpow,
+                               const double* fine_vals, void* stream) {
+    FEMOL_REQUIRE(g && e_base && fine_vals, "femol_gmg_setup: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nd = g->nd;
+    g->lv[0].vals = const_cast<double*>(fine_vals);
+    for (int l = 1; l < g->n_levels; ++l) {
+        Level& F = g->lv[l - 1];
+        Level& C = g->lv[l];
+        int64_t blocks = (C.n_elem + 3) / 4;
+        const int64_t cap = (int64_t)femol_sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        if (nd == 2) {
+            if (l == 1) coarsen_elements<2, true><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, nullptr, e_base, e_coat, xpow, F.fixed, C.ke);
+            else coarsen_elements<2, false><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, F.ke, nullptr, nullptr, nullptr, F.fixed, C.ke);
+        } else {
+            if (l == 1) coarsen_elements<6, true><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, nullptr, e_base, e_coat, xpow, F.fixed, C.ke);
+            else coarsen_elements<6, false><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, F.ke, nullptr, nullptr, nullptr, F.fixed, C.ke);
+        }
+        FEMOL_LAUNCH_CHECK();
+        int rc = femol_assemble(C.plan, C.ke, 1, nullptr, 0, nullptr, 1.0, C.fixed, nullptr, C.vals, st);
+        if (rc != FEMOL_OK) return rc;
+    }
+    for (int l = 0; l < g->n_levels - 1; ++l) {
+        int rc = femol_precond_setup(g->lv[l].plan, g->lv[l].vals, FEMOL_PRECOND_BLOCK_JACOBI, g->lv[l].dinv, st);
+        if (rc != FEMOL_OK) return rc;
+    }
+    Level& CL = g->lv[g->n_levels - 1];
+    FEMOL_CUDA_CHECK(cudaMemsetAsync(g->coarse_inv, 0, CL.n * CL.n * sizeof(double), st));
+    csr_to_dense<<<grid_for(CL.n), 256, 0, st>>>(CL.n, CL.plan->adj_ptr, CL.plan->adj_idx, nd, CL.vals, g->coarse_inv);
+    FEMOL_LAUNCH_CHECK();
+    dense_inverse<<<1, 1024, 0, st>>>((int)CL.n, g->coarse_inv);
+    FEMOL_LAUNCH_CHECK();
+    return FEMOL_OK;
+}
+
+extern "C" int femol_gmg_info(femol_gmg* g, int64_t* h_info /* [0]=levels, then (nx, ny) per level */) {
+    FEMOL_REQUIRE(g && h_info, "femol_gmg_info: null argument");
+    h_info[0] = g->n_levels;
+    for (int l = 0; l < g->n_levels; ++l) { h_info[1 + 2 * l] = g->lv[l].nx; h_info[2 + 2 * l] = g->lv[l].ny; }
+    return FEMOL_OK;
+}
+
+// z = V-cycle(r): one application of the preconditioner (exposed for tests and for LOBPCG)
+extern "C" int femol_gmg_apply(femol_gmg* g, const double* r, double* z, void* stream) {
+    FEMOL_REQUIRE(g && r && z, "femol_gmg_apply: null argument");
+    return femol_gmg_vcycle_internal(g, r, z, (cudaStream_t)stream);
+}

@@ -288,3 +288,158 @@ extern "C" int femol_pcg(femol_plan_t p, const double* vals, const double* f, do
     femol_set_error("femol_pcg: unsupported (ndof=%d, precond=%d)", p->ndof, precond);
     return FEMOL_E_ARG;
 }
+
+// =====================================================================================================
+// PCG with the geometric-multigrid V-cycle as preconditioner (gmg.cu).  Same device-scalar scheme as above;
+// z = V(r) is a sequence of launches between the update and the direction kernels, so z is stored.
+// =====================================================================================================
+struct femol_gmg;
+int femol_gmg_vcycle_internal(femol_gmg* g, const double* r, double* z, cudaStream_t st);
+
+namespace {
+
+// r = f - q ; rr = r.r ; ff = f.f
+__global__ void __launch_bounds__(VEC_THREADS)
+gpcg_init(int64_t n, const double* __restrict__ f, const double* __restrict__ q, double* __restrict__ r,
+          double* __restrict__ sc, double* __restrict__ red_ws, double rtol, int restart) {
+    __shared__ double s_red[32 * 2];
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double fv = f[i], rv = fv - q[i];
+        r[i] = rv;
+        acc[0] += rv * rv; acc[1] += fv * fv;
+    }
+    if (grid_sum_last<2>(acc, red_ws, red_ticket(red_ws), s_red)) {
+        sc[S_RR] = acc[0]; sc[S_FF] = acc[1];
+        sc[S_TOL2] = rtol * rtol * acc[1];
+        if (!restart) sc[S_ITER] = 0.0;
+        sc[S_DONE] = (acc[0] <= rtol * rtol * acc[1]) ? 1.0 : 0.0;
+    }
+}
+
+// slot = r.z
+__global__ void __launch_bounds__(VEC_THREADS)
+gpcg_dot(int64_t n, const double* __restrict__ r, const double* __restrict__ z, double* __restrict__ sc, int slot,
+         double* __restrict__ red_ws) {
+    if (sc[S_DONE] != 0.0) return;
+    __shared__ double s_red[32];
+    double acc[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc[0] += r[i] * z[i];
+    if (grid_sum_last<1>(acc, red_ws, red_ticket(red_ws), s_red)) sc[slot] = acc[0];
+}
+
+// u += alpha p ; r -= alpha q ; rr
+__global__ void __launch_bounds__(VEC_THREADS)
+gpcg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ u,
+            double* __restrict__ r, double* __restrict__ sc, double* __restrict__ red_ws, int parity) {
+    if (sc[S_DONE] != 0.0) return;
+    __shared__ double s_red[32];
+    const double rz = sc[parity ? S_RZ1 : S_RZ0], pq = sc[S_PQ];
+    const double alpha = rz / pq;
+    double acc[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        u[i] += alpha * p[i];
+        const double rv = r[i] - alpha * q[i];
+        r[i] = rv;
+        acc[0] += rv * rv;
+    }
+    if (grid_sum_last<1>(acc, red_ws, red_ticket(red_ws), s_red)) {
+        sc[S_RR] = acc[0];
+        sc[S_ITER] += 1.0;
+        if (!(pq > 0.0) || !(acc[0] == acc[0])) sc[S_DONE] = 2.0;
+        else if (acc[0] <= sc[S_TOL2]) sc[S_DONE] = 1.0;
+    }
+}
+
+// first: p = z ; else p = z + (rz_new / rz_old) p
+__global__ void __launch_bounds__(VEC_THREADS)
+gpcg_direction(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ sc, int parity, int first) {
+    if (sc[S_DONE] != 0.0) return;
+    const double beta = first ? 0.0 : sc[parity ? S_RZ0 : S_RZ1] / sc[parity ? S_RZ1 : S_RZ0];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = first ? z[i] : z[i] + beta * p[i];
+}
+
+}  // namespace
+
+extern "C" int64_t femol_pcg_gmg_workspace_doubles(femol_plan_t p) {
+    if (!p) return 0;
+    return 4 * p->n_nodes * p->ndof + S_NSLOT + FEMOL_RED_WS_DOUBLES;
+}
+
+extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* vals, const double* f, double* u, double rtol,
+                             int max_iter, double* ws, int* h_iters, double* h_relres, void* stream) {
+    FEMOL_REQUIRE(plan && gmg && vals && f && u && ws, "femol_pcg_gmg: null argument");
+    FEMOL_REQUIRE(rtol > 0.0 && max_iter >= 0, "femol_pcg_gmg: bad tolerance / iteration limit");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = plan->n_nodes * plan->ndof;
+    double* r = ws;
+    double* p = r + n;
+    double* q = p + n;
+    double* z = q + n;
+    double* sc = z + n;
+    double* red = sc + S_NSLOT;
+    const int vgrid = femol_grid_for(n, VEC_THREADS, plan->sm_count, 8);
+    FEMOL_CUDA_CHECK(cudaMemsetAsync(sc, 0, (S_NSLOT + FEMOL_RED_WS_DOUBLES) * sizeof(double), st));
+    double h_sc[S_NSLOT];
+    int total_iters = 0, status = FEMOL_S_NOT_CONVERGED;
+    double true_rel = 0.0, prev_true_rel = 1e300;
+    const int batch = 4;
+    for (int restart = 0; restart < 6; ++restart) {
+        int rc = femol_spmv_launch(plan, vals, u, q, nullptr, nullptr, nullptr, st);
+        if (rc != FEMOL_OK) return rc;
+        gpcg_init<<<vgrid, VEC_THREADS, 0, st>>>(n, f, q, r, sc, red, rtol, restart);
+        FEMOL_LAUNCH_CHECK();
+        FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+        FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
+        const double ff = h_sc[S_FF];
+        true_rel = ff > 0.0 ? sqrt(h_sc[S_RR] / ff) : 0.0;
+        if (h_sc[S_DONE] == 1.0 || ff == 0.0) { status = FEMOL_OK; break; }
+        if (restart > 0 && true_rel <= 10.0 * rtol) { status = FEMOL_OK; break; }
+        if (restart > 1 && true_rel >= 0.5 * prev_true_rel) { status = FEMOL_S_STAGNATED; break; }
+        prev_true_rel = true_rel;
+        if (total_iters >= max_iter) break;
+        // z = V(r), rz, p = z
+        rc = femol_gmg_vcycle_internal(gmg, r, z, st);
+        if (rc != FEMOL_OK) return rc;
+        gpcg_dot<<<vgrid, VEC_THREADS, 0, st>>>(n, r, z, sc, S_RZ0, red);
+        gpcg_direction<<<vgrid, VEC_THREADS, 0, st>>>(n, z, p, sc, 0, 1);
+        FEMOL_LAUNCH_CHECK();
+        int parity = 0;
+        bool finished = false;
+        while (!finished && total_iters < max_iter) {
+            const int nb = (max_iter - total_iters) < batch ? (max_iter - total_iters) : batch;
+            for (int it = 0; it < nb; ++it) {
+                rc = femol_spmv_launch(plan, vals, p, q, p, sc + S_PQ, red, st);
+                if (rc != FEMOL_OK) return rc;
+                gpcg_update<<<vgrid, VEC_THREADS, 0, st>>>(n, p, q, u, r, sc, red, parity);
+                FEMOL_LAUNCH_CHECK();
+                rc = femol_gmg_vcycle_internal(gmg, r, z, st);
+                if (rc != FEMOL_OK) return rc;
+                gpcg_dot<<<vgrid, VEC_THREADS, 0, st>>>(n, r, z, sc, parity ? S_RZ0 : S_RZ1, red);
+                gpcg_direction<<<vgrid, VEC_THREADS, 0, st>>>(n, z, p, sc, parity, 0);
+                FEMOL_LAUNCH_CHECK();
+                parity ^= 1;
+            }
+            FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+            FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
+            total_iters = (int)h_sc[S_ITER];
+            if (h_sc[S_DONE] == 2.0) { status = FEMOL_S_BREAKDOWN; finished = true; }
+            else if (h_sc[S_DONE] == 1.0) finished = true;
+        }
+        if (status == FEMOL_S_BREAKDOWN || !finished) break;
+    }
+    if (status == FEMOL_S_NOT_CONVERGED) {
+        int rc = femol_spmv_launch(plan, vals, u, q, nullptr, nullptr, nullptr, st);
+        if (rc != FEMOL_OK) return rc;
+        gpcg_init<<<vgrid, VEC_THREADS, 0, st>>>(n, f, q, r, sc, red, rtol, 1);
+        FEMOL_LAUNCH_CHECK();
+        FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+        FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
+        true_rel = h_sc[S_FF] > 0.0 ? sqrt(h_sc[S_RR] / h_sc[S_FF]) : 0.0;
+        if (true_rel <= 10.0 * rtol) status = FEMOL_OK;
+    }
+    if (h_iters) *h_iters = total_iters;
+    if (h_relres) *h_relres = true_rel;
+    return status;
+}

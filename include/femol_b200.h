@@ -115,6 +115,26 @@ int64_t femol_pcg_workspace_doubles(femol_plan_t plan);
 int femol_pcg(femol_plan_t plan, const double* vals, const double* f, double* u, double rtol,
               int max_iter, int precond, double* ws, int* h_iters, double* h_relres, void* stream);
 
+/* ---- K5b: geometric-multigrid preconditioned CG for structured Q4 meshes -----------------------------------
+ * (SURVEY §7 "hard parts": the PCG iteration count, not bandwidth, decides SIMP iterations/s.)
+ * The mesh must be the reference's rectangle_Q4 ordering (mesh.py:852-860): nodes x-fastest, element e = i*ny+j.
+ * femol_gmg_create builds the level hierarchy (ceil(n/2) coarsening, plans, Dirichlet masks) once;
+ * femol_gmg_setup rebuilds the Galerkin coarse operators element-wise for the current densities:
+ *   solid: child matrices xpow_e * e_base ; coating: e_base + xpow_e * e_coat (xpow = x^p as left in the
+ *   femol_assemble workspace; NULL = no scaling); fine_vals = the assembled fine CSR values.
+ * femol_pcg_gmg = femol_pcg with one V-cycle (nu pre/post damped block-Jacobi sweeps) as preconditioner. */
+typedef struct femol_gmg* femol_gmg_t;
+int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t fine_plan, const uint8_t* fine_fixed,
+                     int nu, double omega, void* stream, femol_gmg_t* out);
+int femol_gmg_destroy(femol_gmg_t gmg);
+int femol_gmg_setup(femol_gmg_t gmg, const double* e_base, const double* e_coat, const double* xpow,
+                    const double* fine_vals, void* stream);
+int femol_gmg_info(femol_gmg_t gmg, int64_t* h_info); /* [0] = levels, then (nx, ny) per level */
+int femol_gmg_apply(femol_gmg_t gmg, const double* r, double* z, void* stream); /* z = V-cycle(r) */
+int64_t femol_pcg_gmg_workspace_doubles(femol_plan_t plan);
+int femol_pcg_gmg(femol_plan_t plan, femol_gmg_t gmg, const double* vals, const double* f, double* u, double rtol,
+                  int max_iter, double* ws, int* h_iters, double* h_relres, void* stream);
+
 /* ---- K6: block kernels for LOBPCG (replaces the dense eigh(K, M) of FEM.py:277 / eigsh of FEM.py:234) ----
  * The Rayleigh-Ritz outer iteration (3m x 3m pencil, m <= 16) is host logic (femol_b200/lobpcg.py); all
  * O(n) work is here.  Block vectors are row-major [n][ld] (the m values of one dof contiguous).
