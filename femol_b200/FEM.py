@@ -128,8 +128,8 @@ class FEM_Problem(object):
         # 'auto': geometric multigrid on rectangle_Q4-ordered structured meshes, block-Jacobi otherwise;
         # 'gmg' | 'block_jacobi' | 'jacobi' | 'none' force one
         self.preconditioner = 'auto'
-        self.gmg_smoothing_steps = 2
-        self.gmg_omega = 0.6
+        self.gmg_smoothing_steps = 1     # pre = post sweeps of damped block-Jacobi (tuned on cfg 2, tools/tune_gmg.py)
+        self.gmg_omega = 0.7
         self.warm_start = True
         self.n_modes = 10
         self.modal_tol = 1e-8
@@ -150,6 +150,9 @@ class FEM_Problem(object):
         self._X_modal = None  # last eigenvector block (warm start)
         self._mask_key = None
         self._mask_dev = None
+        self._fixed_dofs = None
+        self._fixed_dofs_key = None
+        self._F_key = None
         self._grid_shape = None
         self._gmg = None
         self._gmg_mask_key = None
@@ -224,17 +227,25 @@ class FEM_Problem(object):
             self._dev = _Device(self.mesh, self.N_dof)
         return self._dev
 
+    def _bc_key(self):
+        return (len(self.fixed_domains), tuple(tuple(np.asarray(d).tolist()) for d in self.fixed_ddls))
+
     def fixed_dofs(self):
-        """Sorted unique global dof numbers fixed by the registered domains."""
-        out = []
-        for domain, ddls in zip(self.fixed_domains, self.fixed_ddls):
-            nodes = self.mesh.domain_nodes(domain)
-            out.append((nodes[:, None] * self.N_dof + np.asarray(ddls)[None]).reshape(-1))
-        return np.unique(np.concatenate(out)) if out else np.zeros(0, dtype=np.int64)
+        """Sorted unique global dof numbers fixed by the registered domains (cached: the reference
+        re-evaluates every domain predicate over all nodes on each assembly, mesh.py:281)."""
+        key = self._bc_key()
+        if self._fixed_dofs_key != key:
+            out = []
+            for domain, ddls in zip(self.fixed_domains, self.fixed_ddls):
+                nodes = self.mesh.domain_nodes(domain)
+                out.append((nodes[:, None] * self.N_dof + np.asarray(ddls)[None]).reshape(-1))
+            self._fixed_dofs = np.unique(np.concatenate(out)) if out else np.zeros(0, dtype=np.int64)
+            self._fixed_dofs_key = key
+        return self._fixed_dofs
 
     def _fixed_mask(self):
         """uint8 per node, bit d = dof d fixed (device), or None."""
-        key = (len(self.fixed_domains), tuple(tuple(np.asarray(d).tolist()) for d in self.fixed_ddls))
+        key = self._bc_key()
         if key != self._mask_key:
             mask = np.zeros(self.mesh.N_nodes, dtype=np.uint8)
             nodes_all = []
@@ -307,9 +318,14 @@ class FEM_Problem(object):
 
     def _assemble_F(self):
         """FEM.py:536-544: zero the force at fixed dofs."""
+        # id + checksum: catches both re-binding (add_forces) and in-place edits of problem.F
+        key = (self._bc_key(), len(self.forces), id(self.F), float(np.add.reduce(self.F)))
+        if self._F_key == key:
+            return                                   # nothing changed since the last upload
         if self.fixed_ddls:
             self.F[self.fixed_dofs()] = 0
         self._F_dev = torch.from_numpy(np.ascontiguousarray(self.F, dtype=np.float64)).to(self.device.dev)
+        self._F_key = key
 
     @property
     def K(self):

@@ -45,6 +45,12 @@ SIGNATURES = {
     'femol_gmg_apply': (c_int, [P, P, P, P]),
     'femol_pcg_gmg_workspace_doubles': (c_i64, [P]),
     'femol_pcg_gmg': (c_int, [P, P, P, P, P, c_dbl, c_int, P, ctypes.POINTER(c_int), ctypes.POINTER(c_dbl), P]),
+    'femol_dist_unique_id': (c_int, [P]),
+    'femol_dist_init': (c_int, [P, c_int, c_int, ctypes.POINTER(c_vp)]),
+    'femol_dist_destroy': (c_int, [P]),
+    'femol_pcg_dist_workspace_doubles': (c_i64, [P, c_i64]),
+    'femol_pcg_dist': (c_int, [P, P, c_i64, c_int, P, P, P, P, P, P, P, P, c_dbl, c_int, c_int, P,
+                       ctypes.POINTER(c_int), ctypes.POINTER(c_dbl), P]),
     'femol_spmm': (c_int, [P, P, P, c_int, P, c_int, c_int, P]),
     'femol_gram_workspace_doubles': (c_i64, [c_int, c_int]),
     'femol_gram': (c_int, [c_i64, c_int, c_int, P, c_int, P, c_int, P, P, P]),

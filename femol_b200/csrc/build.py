@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
-SOURCES = ['plan.cu', 'elements.cu', 'assemble.cu', 'spmv.cu', 'pcg.cu', 'simp.cu', 'lobpcg.cu', 'gmg.cu']
+SOURCES = ['plan.cu', 'elements.cu', 'assemble.cu', 'spmv.cu', 'pcg.cu', 'simp.cu', 'lobpcg.cu', 'gmg.cu', 'dist.cu']
 HEADERS = ['common.cuh', 'spmv.cuh', os.path.join(ROOT, 'include', 'femol_b200.h')]
 OUT = os.path.join(PKG, 'libfemol_b200.so')
 OBJ_DIR = os.path.join(HERE, 'build')
@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed')
-    cmd = [NVCC, '-shared', '-o', OUT] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+    cmd = [NVCC, '-shared', '-o', OUT] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-ldl']
     subprocess.check_call(cmd)
     with open(stamp, 'w') as fh:
         fh.write(digest)

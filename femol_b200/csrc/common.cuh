@@ -20,6 +20,8 @@ void femol_set_error(const char* fmt, ...);
 
 // every kernel launch goes through this: counts the launch and surfaces launch errors
 void femol_count_launch();
+void femol_count_launches(long long k);  // kernels replayed through a CUDA graph
+extern "C" int64_t femol_launch_count(int reset);
 #define FEMOL_LAUNCH_CHECK()                \
     do {                                    \
         femol_count_launch();               \

@@ -1,0 +1,342 @@
+// Multi-GPU row-block partition: distributed block-Jacobi PCG.
+//
+// One process per GPU.  Rank r owns a contiguous range of nodes (structured meshes: strips of node rows) and
+// holds a LOCAL mesh = its owned nodes first, then the ghost nodes of the one halo layer of elements.  The
+// local plan / assembly are the single-GPU ones (halo elements are assembled redundantly, no communication);
+// only the rows of owned nodes are used.  Per CG iteration:
+//   halo exchange of p (pack kernel -> ncclSend/ncclRecv straight into the ghost segment of p)
+//   q = K p on owned rows, local p.q          -> ncclAllReduce (1 double, in stream)
+//   u += a p, r -= a q, z = M^-1 r, local r.z, r.r -> ncclAllReduce (2 doubles)
+//   p = z + b p
+// All scalars stay on the device; the host reads one flag per batch of iterations.  NCCL is loaded with
+// dlopen at femol_dist_init so that libfemol_b200.so has no link-time NCCL dependency (it is the library
+// torch already loaded in the process when there is one).
+#include <dlfcn.h>
+#include <math.h>
+#include <string.h>
+#include "common.cuh"
+#include "spmv.cuh"
+
+namespace {
+
+// minimal NCCL surface (nccl.h is not included: the .so must build where NCCL is absent)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclDouble_ = 8, ncclSum_ = 0 };  // ncclFloat64 = 8, ncclSum = 0 (stable since NCCL 2.0)
+
+struct NcclApi {
+    void* handle;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    const char* (*GetErrorString)(ncclResult_t);
+};
+NcclApi g_nccl = {};
+
+int load_nccl() {
+    if (g_nccl.handle) return FEMOL_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { femol_set_error("femol_dist: cannot dlopen libnccl.so.2 (%s)", dlerror()); return FEMOL_E_ARG; }
+#define NSYM(field, sym)                                                                  \
+    *(void**)(&g_nccl.field) = dlsym(h, sym);                                             \
+    if (!g_nccl.field) { femol_set_error("femol_dist: symbol %s missing in libnccl", sym); return FEMOL_E_ARG; }
+    NSYM(GetUniqueId, "ncclGetUniqueId") NSYM(CommInitRank, "ncclCommInitRank") NSYM(CommDestroy, "ncclCommDestroy")
+    NSYM(AllReduce, "ncclAllReduce") NSYM(Send, "ncclSend") NSYM(Recv, "ncclRecv") NSYM(GroupStart, "ncclGroupStart")
+    NSYM(GroupEnd, "ncclGroupEnd") NSYM(GetErrorString, "ncclGetErrorString")
+#undef NSYM
+    g_nccl.handle = h;
+    return FEMOL_OK;
+}
+
+#define NCCL_CHECK(expr)                                                                              \
+    do {                                                                                              \
+        ncclResult_t _r = (expr);                                                                     \
+        if (_r != 0) {                                                                                \
+            femol_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, g_nccl.GetErrorString(_r)); \
+            return FEMOL_E_CUDA;                                                                      \
+        }                                                                                             \
+    } while (0)
+
+}  // namespace
+
+struct femol_comm {
+    ncclComm_t comm;
+    int rank, nranks;
+};
+
+namespace {
+
+enum { D_RZ0 = 0, D_RZ1 = 1, D_PQ = 2, D_RR = 3, D_FF = 4, D_DONE = 5, D_ITER = 6, D_TOL2 = 7, D_L0 = 8, D_L1 = 9, D_L2 = 10, D_NSLOT = 16 };
+constexpr int DT = 256;
+
+__global__ void pack_nodes(int64_t n_send, int nd, const int32_t* __restrict__ nodes, const double* __restrict__ x,
+                           double* __restrict__ buf) {
+    const int64_t total = n_send * nd;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = t / nd;
+        buf[t] = x[(int64_t)nodes[k] * nd + (t - k * nd)];
+    }
+}
+
+// z = M^-1 r for one node (block-Jacobi inverse or diagonal stored as full blocks)
+template <int ND>
+__device__ __forceinline__ void prec(const double* __restrict__ dinv, int64_t i, const double (&r)[ND], double (&z)[ND]) {
+    const double* B = dinv + i * ND * ND;
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < ND; ++b) s += __ldg(&B[a * ND + b]) * r[b];
+        z[a] = s;
+    }
+}
+
+// r = f - q ; z = M^-1 r ; p = z ; local sums (r.z, r.r, f.f) -> sc[D_L0..2]
+template <int ND>
+__global__ void __launch_bounds__(DT)
+dpcg_init(int64_t n_owned, const double* __restrict__ f, const double* __restrict__ q, const double* __restrict__ dinv,
+          double* __restrict__ r, double* __restrict__ p, double* __restrict__ sc, double* __restrict__ red) {
+    __shared__ double s_red[32 * 3];
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_owned; i += (int64_t)gridDim.x * blockDim.x) {
+        double rv[ND], zv[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { const double fv = f[i * ND + d]; rv[d] = fv - q[i * ND + d]; acc[2] += fv * fv; }
+        prec<ND>(dinv, i, rv, zv);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { r[i * ND + d] = rv[d]; p[i * ND + d] = zv[d]; acc[0] += rv[d] * zv[d]; acc[1] += rv[d] * rv[d]; }
+    }
+    grid_sum_finish<3>(acc, red, red_ticket(red), sc + D_L0, s_red);
+}
+
+__global__ void dpcg_init_finalize(double* sc, double rtol, int restart) {
+    sc[D_RZ0] = sc[D_L0]; sc[D_RZ1] = sc[D_L0];
+    sc[D_RR] = sc[D_L1]; sc[D_FF] = sc[D_L2];
+    sc[D_TOL2] = rtol * rtol * sc[D_L2];
+    if (!restart) sc[D_ITER] = 0.0;
+    sc[D_DONE] = (sc[D_L1] <= rtol * rtol * sc[D_L2]) ? 1.0 : 0.0;
+}
+
+// u += a p ; r -= a q ; local (r.z, r.r) -> sc[D_L0..1]
+template <int ND>
+__global__ void __launch_bounds__(DT)
+dpcg_update(int64_t n_owned, const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ dinv,
+            double* __restrict__ u, double* __restrict__ r, double* __restrict__ sc, double* __restrict__ red) {
+    __shared__ double s_red[32 * 2];
+    const bool done = sc[D_DONE] != 0.0;
+    const int cur = (((long long)sc[D_ITER]) & 1LL) ? D_RZ1 : D_RZ0;
+    const double alpha = done ? 0.0 : sc[cur] / sc[D_PQ];
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_owned; i += (int64_t)gridDim.x * blockDim.x) {
+        double rv[ND], zv[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const int64_t o = i * ND + d;
+            if (!done) u[o] += alpha * p[o];
+            rv[d] = r[o] - alpha * q[o];
+            if (!done) r[o] = rv[d];
+        }
+        prec<ND>(dinv, i, rv, zv);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { acc[0] += rv[d] * zv[d]; acc[1] += rv[d] * rv[d]; }
+    }
+    // every rank must take part in the collective that follows, so the sums are produced even when done
+    grid_sum_finish<2>(acc, red, red_ticket(red), sc + D_L0, s_red);
+}
+
+__global__ void dpcg_update_finalize(double* sc) {
+    if (sc[D_DONE] != 0.0) return;
+    const double pq = sc[D_PQ];
+    const int cur = (((long long)sc[D_ITER]) & 1LL) ? D_RZ1 : D_RZ0;
+    const int oth = cur == D_RZ0 ? D_RZ1 : D_RZ0;
+    sc[oth] = sc[D_L0];
+    sc[D_RR] = sc[D_L1];
+    sc[D_ITER] += 1.0;
+    if (!(pq > 0.0) || !(sc[D_L1] == sc[D_L1])) sc[D_DONE] = 2.0;
+    else if (sc[D_L1] <= sc[D_TOL2]) sc[D_DONE] = 1.0;
+}
+
+// p = z + beta p on owned nodes (beta = rz_new / rz_old; after the finalize the new value sits in the current slot)
+template <int ND>
+__global__ void __launch_bounds__(DT)
+dpcg_direction(int64_t n_owned, const double* __restrict__ r, const double* __restrict__ dinv, double* __restrict__ p,
+               const double* __restrict__ sc) {
+    if (sc[D_DONE] != 0.0) return;
+    const int cur = (((long long)sc[D_ITER]) & 1LL) ? D_RZ1 : D_RZ0;
+    const int oth = cur == D_RZ0 ? D_RZ1 : D_RZ0;
+    const double beta = sc[cur] / sc[oth];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_owned; i += (int64_t)gridDim.x * blockDim.x) {
+        double rv[ND], zv[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) rv[d] = r[i * ND + d];
+        prec<ND>(dinv, i, rv, zv);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) p[i * ND + d] = zv[d] + beta * p[i * ND + d];
+    }
+}
+
+struct Halo {
+    int n_nbr;
+    const int* nbr_rank;
+    const int64_t* send_ptr;      // [n_nbr+1] offsets into send_nodes
+    const int32_t* send_nodes;    // device
+    const int64_t* recv_start;    // [n_nbr] first local (ghost) node of each neighbour's segment
+    const int64_t* recv_count;    // [n_nbr]
+    double* sendbuf;              // device, send_ptr[n_nbr] * nd doubles
+};
+
+int halo_exchange(femol_comm* c, const Halo& h, int nd, double* x, cudaStream_t st) {
+    const int64_t n_send = h.send_ptr[h.n_nbr];
+    if (n_send > 0) {
+        int grid = (int)((n_send * nd + 255) / 256);
+        if (grid > 1184) grid = 1184;
+        pack_nodes<<<grid, 256, 0, st>>>(n_send, nd, h.send_nodes, x, h.sendbuf);
+        FEMOL_LAUNCH_CHECK();
+    }
+    NCCL_CHECK(g_nccl.GroupStart());
+    for (int k = 0; k < h.n_nbr; ++k) {
+        const int64_t cnt = h.send_ptr[k + 1] - h.send_ptr[k];
+        if (cnt > 0) NCCL_CHECK(g_nccl.Send(h.sendbuf + h.send_ptr[k] * nd, (size_t)(cnt * nd), ncclDouble_, h.nbr_rank[k], c->comm, st));
+        if (h.recv_count[k] > 0)
+            NCCL_CHECK(g_nccl.Recv(x + h.recv_start[k] * nd, (size_t)(h.recv_count[k] * nd), ncclDouble_, h.nbr_rank[k], c->comm, st));
+    }
+    NCCL_CHECK(g_nccl.GroupEnd());
+    return FEMOL_OK;
+}
+
+extern "C" int femol_precond_setup(femol_plan_t p, const double* vals, int kind, double* dinv, void* stream);
+
+template <int ND>
+int dpcg_run(femol_plan_t plan, femol_comm* c, int64_t n_owned, const Halo& h, const double* vals, const double* f, double* u,
+             double rtol, int max_iter, int precond, double* ws, int* h_iters, double* h_relres, cudaStream_t st) {
+    const int64_t n_local = plan->n_nodes * ND;
+    double* r = ws;
+    double* p = r + n_local;
+    double* q = p + n_local;
+    double* dinv = q + n_local;
+    double* sc = dinv + plan->n_nodes * ND * ND;
+    double* red = sc + D_NSLOT;
+    const int vgrid = femol_grid_for(n_owned, DT, plan->sm_count, 8);
+    FEMOL_CUDA_CHECK(cudaMemsetAsync(sc, 0, (D_NSLOT + FEMOL_RED_WS_DOUBLES) * sizeof(double), st));
+    FEMOL_CUDA_CHECK(cudaMemsetAsync(p, 0, n_local * sizeof(double), st));
+    int rc = femol_precond_setup(plan, vals, precond, dinv, st);
+    if (rc != FEMOL_OK) return rc;
+    // an SpMV restricted to the owned rows: a "view" plan with n_nodes = n_owned (owned nodes come first)
+    femol_plan owned_view = *plan;
+    owned_view.n_nodes = n_owned;
+
+    double h_sc[D_NSLOT];
+    int total_iters = 0, status = FEMOL_S_NOT_CONVERGED;
+    double true_rel = 0.0, prev_true_rel = 1e300;
+    const int batch = 25;
+    for (int restart = 0; restart < 6; ++restart) {
+        if ((rc = halo_exchange(c, h, ND, u, st)) != FEMOL_OK) return rc;
+        if ((rc = femol_spmv_launch(&owned_view, vals, u, q, nullptr, nullptr, nullptr, st)) != FEMOL_OK) return rc;
+        dpcg_init<ND><<<vgrid, DT, 0, st>>>(n_owned, f, q, dinv, r, p, sc, red);
+        FEMOL_LAUNCH_CHECK();
+        NCCL_CHECK(g_nccl.AllReduce(sc + D_L0, sc + D_L0, 3, ncclDouble_, ncclSum_, c->comm, st));
+        dpcg_init_finalize<<<1, 1, 0, st>>>(sc, rtol, restart);
+        FEMOL_LAUNCH_CHECK();
+        FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+        FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
+        const double ff = h_sc[D_FF];
+        true_rel = ff > 0.0 ? sqrt(h_sc[D_RR] / ff) : 0.0;
+        if (h_sc[D_DONE] == 1.0 || ff == 0.0) { status = FEMOL_OK; break; }
+        if (restart > 0 && true_rel <= 10.0 * rtol) { status = FEMOL_OK; break; }
+        if (restart > 1 && true_rel >= 0.5 * prev_true_rel) { status = FEMOL_S_STAGNATED; break; }
+        prev_true_rel = true_rel;
+        if (total_iters >= max_iter) break;
+        bool finished = false;
+        while (!finished && total_iters < max_iter) {
+            const int nb = (max_iter - total_iters) < batch ? (max_iter - total_iters) : batch;
+            for (int it = 0; it < nb; ++it) {  // every rank enqueues the same collectives, converged or not
+                if ((rc = halo_exchange(c, h, ND, p, st)) != FEMOL_OK) return rc;
+                if ((rc = femol_spmv_launch(&owned_view, vals, p, q, p, sc + D_L0, red, st)) != FEMOL_OK) return rc;
+                NCCL_CHECK(g_nccl.AllReduce(sc + D_L0, sc + D_PQ, 1, ncclDouble_, ncclSum_, c->comm, st));
+                dpcg_update<ND><<<vgrid, DT, 0, st>>>(n_owned, p, q, dinv, u, r, sc, red);
+                FEMOL_LAUNCH_CHECK();
+                NCCL_CHECK(g_nccl.AllReduce(sc + D_L0, sc + D_L0, 2, ncclDouble_, ncclSum_, c->comm, st));
+                dpcg_update_finalize<<<1, 1, 0, st>>>(sc);
+                dpcg_direction<ND><<<vgrid, DT, 0, st>>>(n_owned, r, dinv, p, sc);
+                FEMOL_LAUNCH_CHECK();
+            }
+            FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+            FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
+            total_iters = (int)h_sc[D_ITER];
+            if (h_sc[D_DONE] == 2.0) { status = FEMOL_S_BREAKDOWN; finished = true; }
+            else if (h_sc[D_DONE] == 1.0) finished = true;
+        }
+        if (status == FEMOL_S_BREAKDOWN || !finished) break;
+    }
+    if (h_iters) *h_iters = total_iters;
+    if (h_relres) *h_relres = true_rel;
+    return status;
+}
+
+}  // namespace
+
+extern "C" int femol_dist_unique_id(void* out128) {
+    FEMOL_REQUIRE(out128, "femol_dist_unique_id: null argument");
+    int rc = load_nccl();
+    if (rc != FEMOL_OK) return rc;
+    ncclUniqueId id;
+    NCCL_CHECK(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    return FEMOL_OK;
+}
+
+extern "C" int femol_dist_init(const void* unique_id128, int rank, int nranks, femol_comm** out) {
+    FEMOL_REQUIRE(unique_id128 && out && nranks >= 1 && rank >= 0 && rank < nranks, "femol_dist_init: bad argument");
+    int rc = load_nccl();
+    if (rc != FEMOL_OK) return rc;
+    ncclUniqueId id;
+    memcpy(&id, unique_id128, sizeof(id));
+    femol_comm* c = new femol_comm();
+    c->rank = rank; c->nranks = nranks; c->comm = nullptr;
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+    if (r != 0) { femol_set_error("ncclCommInitRank -> %s", g_nccl.GetErrorString(r)); delete c; return FEMOL_E_CUDA; }
+    *out = c;
+    return FEMOL_OK;
+}
+
+extern "C" int femol_dist_destroy(femol_comm* c) {
+    if (!c) return FEMOL_OK;
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    delete c;
+    return FEMOL_OK;
+}
+
+extern "C" int64_t femol_pcg_dist_workspace_doubles(femol_plan_t p, int64_t n_send_nodes) {
+    if (!p) return 0;
+    const int64_t n = p->n_nodes * p->ndof;
+    return 3 * n + n * p->ndof + D_NSLOT + FEMOL_RED_WS_DOUBLES + n_send_nodes * p->ndof + 16;
+}
+
+extern "C" int femol_pcg_dist(femol_plan_t plan, femol_comm* comm, int64_t n_owned_nodes, int n_nbr, const int* h_nbr_rank,
+                              const int64_t* h_send_ptr, const int32_t* d_send_nodes, const int64_t* h_recv_start,
+                              const int64_t* h_recv_count, const double* vals, const double* f, double* u, double rtol,
+                              int max_iter, int precond, double* ws, int* h_iters, double* h_relres, void* stream) {
+    FEMOL_REQUIRE(plan && comm && vals && f && u && ws && n_nbr >= 0, "femol_pcg_dist: null argument");
+    FEMOL_REQUIRE(n_owned_nodes >= 0 && n_owned_nodes <= plan->n_nodes, "femol_pcg_dist: bad owned node count");
+    FEMOL_REQUIRE(n_nbr == 0 || (h_nbr_rank && h_send_ptr && h_recv_start && h_recv_count), "femol_pcg_dist: missing halo arrays");
+    FEMOL_REQUIRE(precond >= 0 && precond <= 2 && rtol > 0.0, "femol_pcg_dist: bad preconditioner / tolerance");
+    static const int64_t zero_ptr[1] = {0};
+    Halo h;
+    h.n_nbr = n_nbr; h.nbr_rank = h_nbr_rank; h.send_ptr = n_nbr ? h_send_ptr : zero_ptr; h.send_nodes = d_send_nodes;
+    h.recv_start = h_recv_start; h.recv_count = h_recv_count;
+    const int64_t n = plan->n_nodes * plan->ndof;
+    h.sendbuf = ws + 3 * n + n * plan->ndof + D_NSLOT + FEMOL_RED_WS_DOUBLES;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->ndof == 2) return dpcg_run<2>(plan, comm, n_owned_nodes, h, vals, f, u, rtol, max_iter, precond, ws, h_iters, h_relres, st);
+    if (plan->ndof == 6) return dpcg_run<6>(plan, comm, n_owned_nodes, h, vals, f, u, rtol, max_iter, precond, ws, h_iters, h_relres, st);
+    femol_set_error("femol_pcg_dist: unsupported ndof %d", plan->ndof);
+    return FEMOL_E_ARG;
+}

@@ -24,7 +24,7 @@ extern "C" int femol_precond_setup(femol_plan_t p, const double* vals, int kind,
 namespace {
 
 constexpr int GMG_MAX_LEVELS = 20;
-constexpr int GMG_COARSE_MAX_DOF = 320;
+constexpr int GMG_COARSE_MAX_DOF = 100;
 
 struct Level {
     int64_t nx, ny, n_nodes, n_elem, n;

@@ -291,12 +291,19 @@ extern "C" int femol_pcg(femol_plan_t p, const double* vals, const double* f, do
 
 // =====================================================================================================
 // PCG with the geometric-multigrid V-cycle as preconditioner (gmg.cu).  Same device-scalar scheme as above;
-// z = V(r) is a sequence of launches between the update and the direction kernels, so z is stored.
+// z = V(r) is a sequence of ~100 small launches between the update and the direction kernels, so z is
+// stored and ONE CG iteration (SpMV, update, V-cycle, dot, direction) is captured into a CUDA graph per
+// solve and replayed: the launch-bound coarse levels then cost ~1 us per kernel instead of a host launch.
+// The r.z slots alternate with the device iteration counter, so the captured launch sequence is static.
 // =====================================================================================================
+#include <stdlib.h>
 struct femol_gmg;
 int femol_gmg_vcycle_internal(femol_gmg* g, const double* r, double* z, cudaStream_t st);
 
 namespace {
+
+__device__ __forceinline__ int rz_cur(const double* sc) { return (((long long)sc[S_ITER]) & 1LL) ? S_RZ1 : S_RZ0; }
+__device__ __forceinline__ int rz_other(const double* sc) { return (((long long)sc[S_ITER]) & 1LL) ? S_RZ0 : S_RZ1; }
 
 // r = f - q ; rr = r.r ; ff = f.f
 __global__ void __launch_bounds__(VEC_THREADS)
@@ -317,24 +324,24 @@ gpcg_init(int64_t n, const double* __restrict__ f, const double* __restrict__ q,
     }
 }
 
-// slot = r.z
+// rz[current slot] = r.z
 __global__ void __launch_bounds__(VEC_THREADS)
-gpcg_dot(int64_t n, const double* __restrict__ r, const double* __restrict__ z, double* __restrict__ sc, int slot,
+gpcg_dot(int64_t n, const double* __restrict__ r, const double* __restrict__ z, double* __restrict__ sc,
          double* __restrict__ red_ws) {
     if (sc[S_DONE] != 0.0) return;
     __shared__ double s_red[32];
     double acc[1] = {0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc[0] += r[i] * z[i];
-    if (grid_sum_last<1>(acc, red_ws, red_ticket(red_ws), s_red)) sc[slot] = acc[0];
+    if (grid_sum_last<1>(acc, red_ws, red_ticket(red_ws), s_red)) sc[rz_cur(sc)] = acc[0];
 }
 
-// u += alpha p ; r -= alpha q ; rr
+// u += alpha p ; r -= alpha q ; rr ; iteration counter (flips the r.z slot) ; convergence flag
 __global__ void __launch_bounds__(VEC_THREADS)
 gpcg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ u,
-            double* __restrict__ r, double* __restrict__ sc, double* __restrict__ red_ws, int parity) {
+            double* __restrict__ r, double* __restrict__ sc, double* __restrict__ red_ws) {
     if (sc[S_DONE] != 0.0) return;
     __shared__ double s_red[32];
-    const double rz = sc[parity ? S_RZ1 : S_RZ0], pq = sc[S_PQ];
+    const double rz = sc[rz_cur(sc)], pq = sc[S_PQ];
     const double alpha = rz / pq;
     double acc[1] = {0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -353,11 +360,29 @@ gpcg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ 
 
 // first: p = z ; else p = z + (rz_new / rz_old) p
 __global__ void __launch_bounds__(VEC_THREADS)
-gpcg_direction(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ sc, int parity, int first) {
+gpcg_direction(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ sc, int first) {
     if (sc[S_DONE] != 0.0) return;
-    const double beta = first ? 0.0 : sc[parity ? S_RZ0 : S_RZ1] / sc[parity ? S_RZ1 : S_RZ0];
+    const double beta = first ? 0.0 : sc[rz_cur(sc)] / sc[rz_other(sc)];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = first ? z[i] : z[i] + beta * p[i];
+}
+
+struct GpcgCtx {
+    femol_plan_t plan; femol_gmg* gmg; const double* vals; double *u, *r, *p, *q, *z, *sc, *red; int64_t n; int vgrid;
+};
+
+int gpcg_iteration(const GpcgCtx& c, cudaStream_t st) {
+    int rc = femol_spmv_launch(c.plan, c.vals, c.p, c.q, c.p, c.sc + S_PQ, c.red, st);
+    if (rc != FEMOL_OK) return rc;
+    gpcg_update<<<c.vgrid, VEC_THREADS, 0, st>>>(c.n, c.p, c.q, c.u, c.r, c.sc, c.red);
+    FEMOL_LAUNCH_CHECK();
+    rc = femol_gmg_vcycle_internal(c.gmg, c.r, c.z, st);
+    if (rc != FEMOL_OK) return rc;
+    gpcg_dot<<<c.vgrid, VEC_THREADS, 0, st>>>(c.n, c.r, c.z, c.sc, c.red);
+    FEMOL_LAUNCH_CHECK();
+    gpcg_direction<<<c.vgrid, VEC_THREADS, 0, st>>>(c.n, c.z, c.p, c.sc, 0);
+    FEMOL_LAUNCH_CHECK();
+    return FEMOL_OK;
 }
 
 }  // namespace
@@ -373,24 +398,25 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
     FEMOL_REQUIRE(rtol > 0.0 && max_iter >= 0, "femol_pcg_gmg: bad tolerance / iteration limit");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = plan->n_nodes * plan->ndof;
-    double* r = ws;
-    double* p = r + n;
-    double* q = p + n;
-    double* z = q + n;
-    double* sc = z + n;
-    double* red = sc + S_NSLOT;
-    const int vgrid = femol_grid_for(n, VEC_THREADS, plan->sm_count, 8);
-    FEMOL_CUDA_CHECK(cudaMemsetAsync(sc, 0, (S_NSLOT + FEMOL_RED_WS_DOUBLES) * sizeof(double), st));
+    GpcgCtx c;
+    c.plan = plan; c.gmg = gmg; c.vals = vals; c.u = u; c.n = n;
+    c.r = ws; c.p = c.r + n; c.q = c.p + n; c.z = c.q + n; c.sc = c.z + n; c.red = c.sc + S_NSLOT;
+    c.vgrid = femol_grid_for(n, VEC_THREADS, plan->sm_count, 8);
+    FEMOL_CUDA_CHECK(cudaMemsetAsync(c.sc, 0, (S_NSLOT + FEMOL_RED_WS_DOUBLES) * sizeof(double), st));
     double h_sc[S_NSLOT];
     int total_iters = 0, status = FEMOL_S_NOT_CONVERGED;
     double true_rel = 0.0, prev_true_rel = 1e300;
-    const int batch = 4;
+    const int batch = 2;
+    const bool use_graph = getenv("FEMOL_NO_GRAPH") == nullptr;
+    cudaGraphExec_t exec = nullptr;
+    long long graph_kernels = 0;
+    auto cleanup = [&]() { if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; } };
     for (int restart = 0; restart < 6; ++restart) {
-        int rc = femol_spmv_launch(plan, vals, u, q, nullptr, nullptr, nullptr, st);
-        if (rc != FEMOL_OK) return rc;
-        gpcg_init<<<vgrid, VEC_THREADS, 0, st>>>(n, f, q, r, sc, red, rtol, restart);
+        int rc = femol_spmv_launch(plan, vals, u, c.q, nullptr, nullptr, nullptr, st);
+        if (rc != FEMOL_OK) { cleanup(); return rc; }
+        gpcg_init<<<c.vgrid, VEC_THREADS, 0, st>>>(n, f, c.q, c.r, c.sc, c.red, rtol, restart);
         FEMOL_LAUNCH_CHECK();
-        FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+        FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, c.sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
         FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
         const double ff = h_sc[S_FF];
         true_rel = ff > 0.0 ? sqrt(h_sc[S_RR] / ff) : 0.0;
@@ -400,28 +426,33 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
         prev_true_rel = true_rel;
         if (total_iters >= max_iter) break;
         // z = V(r), rz, p = z
-        rc = femol_gmg_vcycle_internal(gmg, r, z, st);
-        if (rc != FEMOL_OK) return rc;
-        gpcg_dot<<<vgrid, VEC_THREADS, 0, st>>>(n, r, z, sc, S_RZ0, red);
-        gpcg_direction<<<vgrid, VEC_THREADS, 0, st>>>(n, z, p, sc, 0, 1);
+        rc = femol_gmg_vcycle_internal(gmg, c.r, c.z, st);
+        if (rc != FEMOL_OK) { cleanup(); return rc; }
+        gpcg_dot<<<c.vgrid, VEC_THREADS, 0, st>>>(n, c.r, c.z, c.sc, c.red);
+        gpcg_direction<<<c.vgrid, VEC_THREADS, 0, st>>>(n, c.z, c.p, c.sc, 1);
         FEMOL_LAUNCH_CHECK();
-        int parity = 0;
+        if (use_graph && !exec) {  // capture one CG iteration (static launch sequence) once per solve
+            cudaGraph_t graph = nullptr;
+            const long long before = femol_launch_count(0);
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int crc = gpcg_iteration(c, st);
+                graph_kernels = femol_launch_count(0) - before;
+                femol_count_launches(-graph_kernels);  // captured, not executed
+                const cudaError_t e = cudaStreamEndCapture(st, &graph);
+                if (crc != FEMOL_OK || e != cudaSuccess || !graph ||
+                    cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
+                if (graph) cudaGraphDestroy(graph);
+            }
+            cudaGetLastError();  // a failed capture must not poison later launch checks
+        }
         bool finished = false;
         while (!finished && total_iters < max_iter) {
             const int nb = (max_iter - total_iters) < batch ? (max_iter - total_iters) : batch;
             for (int it = 0; it < nb; ++it) {
-                rc = femol_spmv_launch(plan, vals, p, q, p, sc + S_PQ, red, st);
-                if (rc != FEMOL_OK) return rc;
-                gpcg_update<<<vgrid, VEC_THREADS, 0, st>>>(n, p, q, u, r, sc, red, parity);
-                FEMOL_LAUNCH_CHECK();
-                rc = femol_gmg_vcycle_internal(gmg, r, z, st);
-                if (rc != FEMOL_OK) return rc;
-                gpcg_dot<<<vgrid, VEC_THREADS, 0, st>>>(n, r, z, sc, parity ? S_RZ0 : S_RZ1, red);
-                gpcg_direction<<<vgrid, VEC_THREADS, 0, st>>>(n, z, p, sc, parity, 0);
-                FEMOL_LAUNCH_CHECK();
-                parity ^= 1;
+                if (exec) { FEMOL_CUDA_CHECK(cudaGraphLaunch(exec, st)); femol_count_launches(graph_kernels); }
+                else if ((rc = gpcg_iteration(c, st)) != FEMOL_OK) { cleanup(); return rc; }
             }
-            FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+            FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, c.sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
             FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
             total_iters = (int)h_sc[S_ITER];
             if (h_sc[S_DONE] == 2.0) { status = FEMOL_S_BREAKDOWN; finished = true; }
@@ -429,12 +460,13 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
         }
         if (status == FEMOL_S_BREAKDOWN || !finished) break;
     }
+    cleanup();
     if (status == FEMOL_S_NOT_CONVERGED) {
-        int rc = femol_spmv_launch(plan, vals, u, q, nullptr, nullptr, nullptr, st);
+        int rc = femol_spmv_launch(plan, vals, u, c.q, nullptr, nullptr, nullptr, st);
         if (rc != FEMOL_OK) return rc;
-        gpcg_init<<<vgrid, VEC_THREADS, 0, st>>>(n, f, q, r, sc, red, rtol, 1);
+        gpcg_init<<<c.vgrid, VEC_THREADS, 0, st>>>(n, f, c.q, c.r, c.sc, c.red, rtol, 1);
         FEMOL_LAUNCH_CHECK();
-        FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+        FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, c.sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
         FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
         true_rel = h_sc[S_FF] > 0.0 ? sqrt(h_sc[S_RR] / h_sc[S_FF]) : 0.0;
         if (true_rel <= 10.0 * rtol) status = FEMOL_OK;

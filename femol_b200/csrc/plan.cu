@@ -22,6 +22,7 @@ extern "C" const char* femol_last_error(void) { return g_err; }
 #include <atomic>
 static std::atomic<long long> g_launches{0};
 void femol_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void femol_count_launches(long long k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
 extern "C" int64_t femol_launch_count(int reset) {
     const long long v = g_launches.load();
     if (reset) g_launches.store(0);

@@ -135,6 +135,24 @@ int64_t femol_pcg_gmg_workspace_doubles(femol_plan_t plan);
 int femol_pcg_gmg(femol_plan_t plan, femol_gmg_t gmg, const double* vals, const double* f, double* u, double rtol,
                   int max_iter, double* ws, int* h_iters, double* h_relres, void* stream);
 
+/* ---- multi-GPU row-block partition: distributed block-Jacobi PCG --------------------------------
+ * One process per GPU.  `plan` is the plan of the rank's LOCAL mesh: owned nodes first (a contiguous range of the
+ * global numbering), then the ghost nodes of its one halo layer of elements, grouped by owning rank.  Only the
+ * rows of owned nodes are used.  Halo: for neighbour k, the owned local nodes send_nodes[send_ptr[k]..send_ptr[k+1])
+ * are packed and sent, and recv_count[k] nodes are received straight into the ghost segment starting at local
+ * node recv_start[k].  Dot products are ncclAllReduce'd in stream; scalars never leave the device inside a batch.
+ * NCCL is dlopen'ed (libnccl.so.2): rank 0 calls femol_dist_unique_id, the 128 bytes are broadcast by the host
+ * (torch.distributed), every rank calls femol_dist_init.  vals/f/u are local arrays (u: owned + ghost entries). */
+typedef struct femol_comm* femol_comm_t;
+int femol_dist_unique_id(void* h_out128);
+int femol_dist_init(const void* h_unique_id128, int rank, int nranks, femol_comm_t* out);
+int femol_dist_destroy(femol_comm_t comm);
+int64_t femol_pcg_dist_workspace_doubles(femol_plan_t plan, int64_t n_send_nodes);
+int femol_pcg_dist(femol_plan_t plan, femol_comm_t comm, int64_t n_owned_nodes, int n_nbr, const int* h_nbr_rank,
+                   const int64_t* h_send_ptr, const int32_t* d_send_nodes, const int64_t* h_recv_start,
+                   const int64_t* h_recv_count, const double* vals, const double* f, double* u, double rtol,
+                   int max_iter, int precond, double* ws, int* h_iters, double* h_relres, void* stream);
+
 /* ---- K6: block kernels for LOBPCG (replaces the dense eigh(K, M) of FEM.py:277 / eigsh of FEM.py:234) ----
  * The Rayleigh-Ritz outer iteration (3m x 3m pencil, m <= 16) is host logic (femol_b200/lobpcg.py); all
  * O(n) work is here.  Block vectors are row-major [n][ld] (the m values of one dof contiguous).

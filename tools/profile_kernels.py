@@ -16,7 +16,7 @@ def main():
     nx = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
     ny = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 12
-    problem, opt = bench.build_gpu_problem(F, nx, ny, 1e-8, 'block_jacobi')
+    problem, opt = bench.build_gpu_problem(F, nx, ny, 1e-8, sys.argv[4] if len(sys.argv) > 4 else 'auto')
     problem.solver_max_iter = iters
     g = torch.Generator(device='cuda'); g.manual_seed(0)
     opt.x_device.copy_(torch.rand(problem.device.n_elem, dtype=torch.float64, device='cuda', generator=g) * 0.999 + 0.001)
