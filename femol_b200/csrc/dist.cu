@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "spmv.cuh"
 
+extern "C" int femol_precond_setup(femol_plan_t p, const double* vals, int kind, double* dinv, void* stream);
+
 namespace {
 
 // minimal NCCL surface (nccl.h is not included: the .so must build where NCCL is absent)
@@ -211,8 +213,6 @@ int halo_exchange(femol_comm* c, const Halo& h, int nd, double* x, cudaStream_t 
     NCCL_CHECK(g_nccl.GroupEnd());
     return FEMOL_OK;
 }
-
-extern "C" int femol_precond_setup(femol_plan_t p, const double* vals, int kind, double* dinv, void* stream);
 
 template <int ND>
 int dpcg_run(femol_plan_t plan, femol_comm* c, int64_t n_owned, const Halo& h, const double* vals, const double* f, double* u,

@@ -224,8 +224,15 @@ def test_pcg_dist_two_gpus(nx, ny, model):
     procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, nx, ny, model, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=280) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-    for rank, status, extra in sorted(results):
-        assert status == 'ok', 'rank %d: %s' % (rank, status)
+    results = []
+    try:
+        for _ in procs:
+            results.append(q.get(timeout=150))
+            if results[-1][1] != 'ok':      # a failed rank leaves its peer waiting in a collective: stop now
+                break
+    finally:
+        for p in procs:
+            p.join(timeout=5 if (results and results[-1][1] != 'ok') else 60)
+            if p.is_alive():
+                p.kill()
+    assert len(results) == len(procs) and all(r[1] == 'ok' for r in results), results
