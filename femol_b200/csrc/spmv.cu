@@ -6,6 +6,7 @@
 // traffic per product: 8*nnz (values) + 4*nnz/ndof^2 (adjacency) + 16*n (x once, y once) — 25 % less
 // than plain CSR at ndof = 2 and 33 % less at ndof = 6.
 // femol_spmv_csr: plain CSR product for arbitrary matrices (parity checks against scipy matrices).
+#include <stdlib.h>
 #include "common.cuh"
 #include "spmv.cuh"
 
@@ -31,6 +32,24 @@ spmv_csr_kernel(int64_t n_rows, const int32_t* __restrict__ indptr, const int32_
 }
 
 }  // namespace
+
+size_t femol_l2_persist_bytes() {
+    static long long cached = -1;
+    if (cached >= 0) return (size_t)cached;
+    cached = 0;
+    const char* env = getenv("FEMOL_L2_PERSIST_MB");
+    const long mb = env ? atol(env) : 32;   // default: 32 MB of the 126 MB L2 (measured: SpMV 152 -> 147 us; 96 MB: 235 us)
+    if (mb <= 0) return 0;
+    int dev = 0, max_persist = 0, max_window = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    long long want = (long long)mb << 20;
+    if (want > max_persist) want = max_persist;
+    if (want <= 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cached = want < max_window ? want : max_window;
+    return (size_t)cached;
+}
 
 int femol_spmv_launch(femol_plan_t p, const double* vals, const double* x, double* y, const double* dot_with,
                       double* dot_out, double* red_ws, cudaStream_t st) {

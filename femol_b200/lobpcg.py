@@ -57,6 +57,8 @@ def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False):
     have_p = False
     rel = np.full(m, np.inf)
     it = 0
+    calm = 0            # consecutive iterations without any change of the Ritz values
+    lam_prev = lam.copy()
     for it in range(1, max_iter + 1):
         ops.residual(lam)                                       # R -> W slot
         rn = np.sqrt(np.diag(ops.gram('S', 'S', m, m, m, m)))
@@ -67,6 +69,16 @@ def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False):
         if np.all(rel[:k] <= tol):
             it -= 1
             break
+        # Attainable accuracy: ||K v - l M v|| / ||K v|| cannot drop below ~eps * cond; once the Ritz values
+        # have stopped moving (1e-13 relative, three iterations in a row) further iterations only add noise.
+        if it > 1 and np.all(np.abs(lam[:k] - lam_prev[:k]) <= 1e-13 * np.abs(lam[:k])):
+            calm += 1
+            if calm >= 3:
+                it -= 1
+                break
+        else:
+            calm = 0
+        lam_prev = lam.copy()
         ops.precondition()                                      # W <- T R  (fixed dofs zeroed)
         # M-orthogonalise W against X, then M-orthonormalise W (Cholesky)
         ops.spmm('M', m, m)
@@ -85,11 +97,13 @@ def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False):
         q = q3 if have_p else 2 * m
         A = ops.gram('S', 'KS', 0, q, 0, q)
         B = ops.gram('S', 'MS', 0, q, 0, q)
+        if not (np.isfinite(A).all() and np.isfinite(B).all()):
+            break                                                # keep the last good block
         try:
             lam_new, C = _rayleigh_ritz(A, B, m)
         except (np.linalg.LinAlgError, ValueError):
             if not have_p:
-                raise
+                break
             # ill-conditioned basis: restart without the conjugate directions
             q = 2 * m
             lam_new, C = _rayleigh_ritz(A[:q, :q], B[:q, :q], m)
