@@ -117,7 +117,7 @@ class ClockSampler(object):
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -214,7 +214,6 @@ def run_gpu(args):
     barrier()
     launches = int(L.femol_launch_count(0))
     dt = ev0.elapsed_time(ev1) * 1e-3
-    clocks = sampler.stop() if sampler else None
 
     # ---- end-to-end steps with host buffers ---------------------------------------------------------------
     x_host = torch.empty(n_elem, dtype=torch.float64).pin_memory()
@@ -232,6 +231,7 @@ def run_gpu(args):
     e1.record()
     barrier()
     dt_e2e = e0.elapsed_time(e1) * 1e-3
+    clocks = sampler.stop() if sampler else None   # sampled over both timed regions (device-resident + e2e)
 
     if world > 1:
         t = torch.tensor([dt, dt_e2e], dtype=torch.float64, device='cuda')

@@ -70,10 +70,10 @@ def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False):
             it -= 1
             break
         # Attainable accuracy: ||K v - l M v|| / ||K v|| cannot drop below ~eps * cond; once the Ritz values
-        # have stopped moving (1e-13 relative, three iterations in a row) further iterations only add noise.
-        if it > 1 and np.all(np.abs(lam[:k] - lam_prev[:k]) <= 1e-13 * np.abs(lam[:k])):
+        # have stopped moving (1e-11 relative, two iterations in a row) further iterations only add noise.
+        if it > 1 and np.all(np.abs(lam[:k] - lam_prev[:k]) <= 1e-11 * np.abs(lam[:k])):
             calm += 1
-            if calm >= 3:
+            if calm >= 2:
                 it -= 1
                 break
         else:
