@@ -131,6 +131,9 @@ class FEM_Problem(object):
         self.gmg_smoothing_steps = 1     # pre = post sweeps of damped block-Jacobi (tuned on cfg 2, tools/tune_gmg.py)
         self.gmg_omega = 0.7
         self.warm_start = True
+        # structured rectangle_Q4 grids: PCG / multigrid apply K matrix-free (csrc/stencil.cu); K itself is
+        # still assembled (it is what .K returns and what the block eigen-solver multiplies with)
+        self.matrix_free = True
         self.n_modes = 10
         self.modal_tol = 1e-8
         self.modal_max_iter = 500
@@ -159,6 +162,7 @@ class FEM_Problem(object):
         self._gmg_stale = True
         self._gmg_ws = None
         self._K_scaled = False
+        self._mf_refs = None  # keeps the tensors the plan's matrix-free descriptor borrows alive
 
     def __del__(self):
         try:
@@ -301,6 +305,15 @@ class FEM_Problem(object):
         if which == 'K':
             self._K_scaled = x is not None
             self._gmg_stale = True
+            # structured grids: the solvers apply K from (Ke, x^p, mask) instead of streaming the CSR values
+            shape = self.structured_grid_shape() if self.matrix_free else None
+            if shape:
+                mask = self._fixed_mask()
+                _lib.call('femol_plan_set_matrix_free', d.plan, shape[0], shape[1], _lib.ptr(Eb), _lib.ptr(Ec),
+                          _lib.ptr(xpow) if x is not None else None, _lib.ptr(mask), _lib.ptr(vals))
+                self._mf_refs = (Eb, Ec, xpow, mask, vals)
+            else:
+                _lib.call('femol_plan_set_matrix_free', d.plan, 0, 0, None, None, None, None, None)
         return vals
 
     # ---- assembly -----------------------------------------------------------------------------------

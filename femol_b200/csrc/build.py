@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
-SOURCES = ['plan.cu', 'elements.cu', 'assemble.cu', 'spmv.cu', 'pcg.cu', 'simp.cu', 'lobpcg.cu', 'gmg.cu', 'dist.cu']
+SOURCES = ['plan.cu', 'elements.cu', 'assemble.cu', 'spmv.cu', 'pcg.cu', 'simp.cu', 'lobpcg.cu', 'gmg.cu', 'dist.cu', 'stencil.cu']
 HEADERS = ['common.cuh', 'spmv.cuh', os.path.join(ROOT, 'include', 'femol_b200.h')]
 OUT = os.path.join(PKG, 'libfemol_b200.so')
 OBJ_DIR = os.path.join(HERE, 'build')

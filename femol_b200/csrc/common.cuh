@@ -36,6 +36,14 @@ extern "C" int64_t femol_launch_count(int reset);
         }                                                          \
     } while (0)
 
+// Matrix-free description of K on a structured rectangle_Q4 mesh (stencil.cu); all pointers borrowed.
+struct femol_matrix_free {
+    int64_t nx, ny;
+    const double *e_base, *e_coat, *xpow;
+    const uint8_t* fixed;
+    const double* vals;  // the assembled value array this description is equivalent to (identity tag)
+};
+
 // The symbolic plan (plan.cu).  All pointers are device memory owned by the plan.
 struct femol_plan {
     int64_t n_elem, n_nodes, nnz_node, nnz;
@@ -52,6 +60,7 @@ struct femol_plan {
     uint32_t* src_ell;  // [nnz_node][ell_width] the same lists at fixed width (0xFFFFFFFF = empty), or NULL
     int ell_width;      // 4, 8 or 0 (a node pair with more than 8 contributing elements: lists only)
     int sm_count;
+    femol_matrix_free* mf;  // host struct, optional (femol_plan_set_matrix_free)
 };
 
 // Deterministic grid reduction scratch: FEMOL_RED_SLOTS partial slots + a ticket counter.

@@ -501,7 +501,7 @@ int smooth(femol_gmg* g, int l, const double* r, double* e, bool zero_start, cud
             jacobi_kernel<ND, true><<<grid, 256, 0, st>>>(L.n_nodes, g->omega, L.dinv, r, nullptr, e);
             FEMOL_LAUNCH_CHECK();
         } else {
-            int rc = femol_spmv_launch(L.plan, L.vals, e, L.t, nullptr, nullptr, nullptr, st);
+            int rc = femol_apply_launch(L.plan, L.vals, e, L.t, nullptr, nullptr, nullptr, st);
             if (rc != FEMOL_OK) return rc;
             jacobi_kernel<ND, false><<<grid, 256, 0, st>>>(L.n_nodes, g->omega, L.dinv, r, L.t, e);
             FEMOL_LAUNCH_CHECK();
@@ -526,7 +526,7 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st) {
     Level& C = g->lv[l + 1];
     int rc = smooth<ND>(g, l, r, e, true, st);
     if (rc != FEMOL_OK) return rc;
-    rc = femol_spmv_launch(L.plan, L.vals, e, L.t, nullptr, nullptr, nullptr, st);
+    rc = femol_apply_launch(L.plan, L.vals, e, L.t, nullptr, nullptr, nullptr, st);
     if (rc != FEMOL_OK) return rc;
     residual_kernel<<<grid_for(L.n), 256, 0, st>>>(L.n, r, L.t, L.t);
     FEMOL_LAUNCH_CHECK();

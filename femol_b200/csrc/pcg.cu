@@ -210,7 +210,7 @@ int pcg_run(femol_plan_t plan, const double* vals, const double* f, double* u, d
     const int batch = 50;
     for (int restart = 0; restart < 6; ++restart) {
         // (re)start from the true residual
-        int rc = femol_spmv_launch(plan, vals, u, q, nullptr, nullptr, nullptr, st);
+        int rc = femol_apply_launch(plan, vals, u, q, nullptr, nullptr, nullptr, st);
         if (rc != FEMOL_OK) return rc;
         pcg_init<ND, MODE><<<vgrid, VEC_THREADS, 0, st>>>(n_nodes, f, q, dinv, r, p, sc, red, rtol, restart);
         FEMOL_LAUNCH_CHECK();
@@ -231,7 +231,7 @@ int pcg_run(femol_plan_t plan, const double* vals, const double* f, double* u, d
         while (!finished && total_iters < max_iter) {
             const int nb = (max_iter - total_iters) < batch ? (max_iter - total_iters) : batch;
             for (int it = 0; it < nb; ++it) {
-                rc = femol_spmv_launch(plan, vals, p, q, p, sc + S_PQ, red, st);
+                rc = femol_apply_launch(plan, vals, p, q, p, sc + S_PQ, red, st);
                 if (rc != FEMOL_OK) return rc;
                 pcg_update<ND, MODE><<<vgrid, VEC_THREADS, 0, st>>>(n_nodes, p, q, dinv, u, r, sc, red, parity);
                 pcg_direction<ND, MODE><<<vgrid, VEC_THREADS, 0, st>>>(n_nodes, r, dinv, p, sc, parity);
@@ -251,7 +251,7 @@ int pcg_run(femol_plan_t plan, const double* vals, const double* f, double* u, d
     }
     if (status == FEMOL_S_NOT_CONVERGED) {
         // report the true residual of whatever we have
-        int rc = femol_spmv_launch(plan, vals, u, q, nullptr, nullptr, nullptr, st);
+        int rc = femol_apply_launch(plan, vals, u, q, nullptr, nullptr, nullptr, st);
         if (rc != FEMOL_OK) return rc;
         pcg_init<ND, MODE><<<vgrid, VEC_THREADS, 0, st>>>(n_nodes, f, q, dinv, r, p, sc, red, rtol, 1);
         FEMOL_LAUNCH_CHECK();
@@ -372,7 +372,7 @@ struct GpcgCtx {
 };
 
 int gpcg_iteration(const GpcgCtx& c, cudaStream_t st) {
-    int rc = femol_spmv_launch(c.plan, c.vals, c.p, c.q, c.p, c.sc + S_PQ, c.red, st);
+    int rc = femol_apply_launch(c.plan, c.vals, c.p, c.q, c.p, c.sc + S_PQ, c.red, st);
     if (rc != FEMOL_OK) return rc;
     gpcg_update<<<c.vgrid, VEC_THREADS, 0, st>>>(c.n, c.p, c.q, c.u, c.r, c.sc, c.red);
     FEMOL_LAUNCH_CHECK();
@@ -412,7 +412,7 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
     long long graph_kernels = 0;
     auto cleanup = [&]() { if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; } };
     for (int restart = 0; restart < 6; ++restart) {
-        int rc = femol_spmv_launch(plan, vals, u, c.q, nullptr, nullptr, nullptr, st);
+        int rc = femol_apply_launch(plan, vals, u, c.q, nullptr, nullptr, nullptr, st);
         if (rc != FEMOL_OK) { cleanup(); return rc; }
         gpcg_init<<<c.vgrid, VEC_THREADS, 0, st>>>(n, f, c.q, c.r, c.sc, c.red, rtol, restart);
         FEMOL_LAUNCH_CHECK();
@@ -462,7 +462,7 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
     }
     cleanup();
     if (status == FEMOL_S_NOT_CONVERGED) {
-        int rc = femol_spmv_launch(plan, vals, u, c.q, nullptr, nullptr, nullptr, st);
+        int rc = femol_apply_launch(plan, vals, u, c.q, nullptr, nullptr, nullptr, st);
         if (rc != FEMOL_OK) return rc;
         gpcg_init<<<c.vgrid, VEC_THREADS, 0, st>>>(n, f, c.q, c.r, c.sc, c.red, rtol, 1);
         FEMOL_LAUNCH_CHECK();

@@ -244,6 +244,7 @@ extern "C" int femol_plan_destroy(femol_plan_t p) {
     if (!p) return FEMOL_OK;
     cudaFree(p->conn); cudaFree(p->n2e_ptr); cudaFree(p->n2e_idx); cudaFree(p->adj_ptr); cudaFree(p->adj_idx);
     cudaFree(p->src_ptr); cudaFree(p->src); cudaFree(p->src_ell);
+    delete p->mf;
     delete p;
     return FEMOL_OK;
 }

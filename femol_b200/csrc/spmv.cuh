@@ -97,3 +97,6 @@ int spmv_node_launch(femol_plan_t p, const double* vals, const double* x, double
 
 int femol_spmv_launch(femol_plan_t p, const double* vals, const double* x, double* y, const double* dot_with,
                       double* dot_out, double* red_ws, cudaStream_t st);
+// solver-side K x: matrix-free stencil when available for `vals` (stencil.cu), else the CSR kernel above
+int femol_apply_launch(femol_plan_t p, const double* vals, const double* x, double* y, const double* dot_with,
+                       double* dot_out, double* red_ws, cudaStream_t st);

@@ -40,7 +40,7 @@ def _rayleigh_ritz(A, B, m):
     return w[:m], (T @ c[:, :m]) * d[:, None]
 
 
-def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False):
+def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False, stall_window=2):
     """Run LOBPCG on `ops` (which already holds the initial block in S[:, :m]).
 
     Returns (lambda[m], rel_resid[m], iterations).  On exit ops.S[:, :m] holds M-orthonormal Ritz vectors,
@@ -57,8 +57,8 @@ def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False):
     have_p = False
     rel = np.full(m, np.inf)
     it = 0
-    calm = 0            # consecutive iterations without any change of the Ritz values
     lam_prev = lam.copy()
+    history, calm = [], 0
     for it in range(1, max_iter + 1):
         ops.residual(lam)                                       # R -> W slot
         rn = np.sqrt(np.diag(ops.gram('S', 'S', m, m, m, m)))
@@ -69,11 +69,15 @@ def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False):
         if np.all(rel[:k] <= tol):
             it -= 1
             break
-        # Attainable accuracy: ||K v - l M v|| / ||K v|| cannot drop below ~eps * cond; once the Ritz values
-        # have stopped moving (1e-11 relative, two iterations in a row) further iterations only add noise.
-        if it > 1 and np.all(np.abs(lam[:k] - lam_prev[:k]) <= 1e-11 * np.abs(lam[:k])):
+        # Attainable accuracy: ||K v - l M v|| / ||K v|| cannot drop below ~eps * cond.  Once the Ritz values
+        # have stopped moving (1e-11 relative) AND the worst residual is no longer halving over two iterations,
+        # `stall_window` iterations in a row, further iterations only add noise (the residuals drift up again).
+        worst = float(np.max(rel[:k]))
+        history.append(worst)
+        slow = len(history) >= 3 and worst >= 0.5 * history[-3]
+        if slow and np.all(np.abs(lam[:k] - lam_prev[:k]) <= 1e-11 * np.abs(lam[:k])):
             calm += 1
-            if calm >= 2:
+            if calm >= stall_window:
                 it -= 1
                 break
         else:

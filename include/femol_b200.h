@@ -106,6 +106,16 @@ int femol_spmv(femol_plan_t plan, const double* vals, const double* x, double* y
 int femol_spmv_csr(int64_t n_rows, const int32_t* indptr, const int32_t* indices, const double* vals,
                    const double* x, double* y, void* stream);
 
+/* Matrix-free K for the solvers on structured rectangle_Q4 meshes (nodes x-fastest, element e = i*ny + j):
+ * declares that the value array `vals` equals sum_e (xpow_e * e_base [or e_base + xpow_e * e_coat]) with the
+ * Dirichlet mask `fixed` applied — i.e. the arguments of the femol_assemble call that produced it.  femol_pcg /
+ * femol_pcg_gmg then apply K from these 80 MB instead of streaming the 720 MB of CSR values (cfg 2).  Pointers
+ * are borrowed and must outlive the solves; pass e_base = NULL to clear.  femol_apply = K x through the operator
+ * the solvers use (femol_spmv always uses the CSR values). */
+int femol_plan_set_matrix_free(femol_plan_t plan, int64_t nx, int64_t ny, const double* e_base,
+                               const double* e_coat, const double* xpow, const uint8_t* fixed, const double* vals);
+int femol_apply(femol_plan_t plan, const double* vals, const double* x, double* y, void* stream);
+
 /* ---- K5: preconditioned conjugate gradients (replaces spsolve, FEM.py:258-265) --------------
  * Solves A u = f from the initial guess in u.  ws: femol_pcg_workspace_doubles(plan) doubles.
  * Stops when ||r|| <= rtol*||f|| (recurrence residual; the true residual is re-checked and the
