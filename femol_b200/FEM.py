@@ -147,6 +147,7 @@ class FEM_Problem(object):
         self.solver_info = {}
         self._dev = None
         self._E = {}          # cached element matrices on the device
+        self._E_host = {}     # host copies of the shared (structured-mesh) element matrices
         self._Kv = self._Mv = None
         self._K_host = self._M_host = None
         self._U_dev = None
@@ -179,6 +180,7 @@ class FEM_Problem(object):
         if len(materials) == 2:
             self.coating = True
         self._E.clear()
+        self._E_host.clear()
 
     def define_tensors(self, *tensors):
         """FEM.py:113-154: thickness (isotropic) or Layup (orthotropic), base [+ coating]."""
@@ -202,6 +204,7 @@ class FEM_Problem(object):
             self.coat_ho = ho[1]
             self.coating = True
         self._E.clear()
+        self._E_host.clear()
 
     def add_fixed_domain(self, domain, ddls=None):
         """FEM.py:424-438"""
@@ -292,6 +295,17 @@ class FEM_Problem(object):
             self._E[key] = (E, 0 if self.mesh.structured else 1)
         return self._E[key]
 
+    def _element_matrix_host(self, E):
+        """Host copy of a shared element matrix (one device read per cached matrix, not per assembly)."""
+        if E is None:
+            return None
+        key = (E.data_ptr(), E._version)
+        hit = self._E_host.get(key)
+        if hit is None:
+            # the tensor is kept with its copy so the address cannot be recycled while the entry lives
+            hit = self._E_host[key] = (E, np.ascontiguousarray(E[0].cpu().numpy().reshape(-1)))
+        return hit[1]
+
     def _assemble_values(self, which, X, expo):
         d = self.device
         Eb, pe_b = self._element_matrices(which, False)
@@ -309,9 +323,11 @@ class FEM_Problem(object):
             shape = self.structured_grid_shape() if self.matrix_free else None
             if shape:
                 mask = self._fixed_mask()
-                _lib.call('femol_plan_set_matrix_free', d.plan, shape[0], shape[1], _lib.ptr(Eb), _lib.ptr(Ec),
+                hb, hc = self._element_matrix_host(Eb), self._element_matrix_host(Ec)
+                _lib.call('femol_plan_set_matrix_free', d.plan, shape[0], shape[1], hb.ctypes.data,
+                          hc.ctypes.data if hc is not None else None,
                           _lib.ptr(xpow) if x is not None else None, _lib.ptr(mask), _lib.ptr(vals))
-                self._mf_refs = (Eb, Ec, xpow, mask, vals)
+                self._mf_refs = (xpow, mask, vals)
             else:
                 _lib.call('femol_plan_set_matrix_free', d.plan, 0, 0, None, None, None, None, None)
         return vals

@@ -36,10 +36,13 @@ extern "C" int64_t femol_launch_count(int reset);
         }                                                          \
     } while (0)
 
-// Matrix-free description of K on a structured rectangle_Q4 mesh (stencil.cu); all pointers borrowed.
+// Matrix-free description of K on a structured rectangle_Q4 mesh (stencil.cu); device pointers are borrowed,
+// the element matrices are host copies (they are passed to the kernel as parameters).
 struct femol_matrix_free {
     int64_t nx, ny;
-    const double *e_base, *e_coat, *xpow;
+    double e_base[576], e_coat[576];
+    bool has_coat;
+    const double* xpow;
     const uint8_t* fixed;
     const double* vals;  // the assembled value array this description is equivalent to (identity tag)
 };

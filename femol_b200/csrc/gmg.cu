@@ -44,6 +44,7 @@ struct femol_gmg {
     double omega;
     Level lv[GMG_MAX_LEVELS];
     double* coarse_inv;  // dense inverse of the coarsest operator [nc][nc]
+    double* child_g;     // [2][4][S2] Galerkin images P_c^T Ke P_c of the shared element matrix (base | coat)
     int64_t nc;
     void* d_desc;        // device array of LevelDesc (all levels) for the fused coarse V-cycle
     int fused_from;      // first level handled by the single-CTA kernel (n_levels = none)
@@ -82,13 +83,39 @@ __global__ void coarsen_mask(int64_t nxf, int64_t nyf, const uint8_t* __restrict
 }
 
 // ---- element-wise Galerkin coarsening ----------------------------------------------------------------------
+// G[c] = P_c^T Ke P_c for the four children c = 2 ca + cb of a full parent element (no Dirichlet nodes), base and
+// coating matrix: the level-0 fast path of coarsen_elements combines them with the element densities.
+template <int ND>
+__global__ void child_images(const double* __restrict__ e_base, const double* __restrict__ e_coat, double* __restrict__ G) {
+    constexpr int S = 4 * ND, S2 = S * S;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 8 * S2; t += gridDim.x * blockDim.x) {
+        const int mat = t / (4 * S2), c = (t / S2) & 3, idx = t % S2;
+        const double* ke = mat ? e_coat : e_base;
+        if (!ke) { G[t] = 0.0; continue; }
+        const int ca = c >> 1, cb = c & 1;
+        const double s0 = 0.5 * ca, s1 = 0.5 * (ca + 1), t0 = 0.5 * cb, t1 = 0.5 * (cb + 1);
+        const double ps[4] = {s0, s1, s1, s0}, pt[4] = {t0, t0, t1, t1};
+        const int r = idx / S, cc = idx - r * S;
+        const int p = r / ND, da = r - p * ND, q = cc / ND, db = cc - q * ND;
+        double v = 0.0;
+        for (int a = 0; a < 4; ++a) {
+            const double wa = p == 0 ? (1 - ps[a]) * (1 - pt[a]) : p == 1 ? ps[a] * (1 - pt[a]) : p == 2 ? ps[a] * pt[a] : (1 - ps[a]) * pt[a];
+            for (int b = 0; b < 4; ++b) {
+                const double wb = q == 0 ? (1 - ps[b]) * (1 - pt[b]) : q == 1 ? ps[b] * (1 - pt[b]) : q == 2 ? ps[b] * pt[b] : (1 - ps[b]) * pt[b];
+                v += wa * wb * ke[(a * ND + da) * S + b * ND + db];
+            }
+        }
+        G[t] = v;
+    }
+}
+
 // One warp per coarse element.  LEVEL0: child matrices are x_c^p * Ke (+ coat) from the shared element matrix;
 // otherwise they are the previous level's per-element matrices.
 template <int ND, bool LEVEL0>
 __global__ void __launch_bounds__(128)
 coarsen_elements(int64_t nxf, int64_t nyf, int64_t nxc, int64_t nyc, const double* __restrict__ child_ke,
                  const double* __restrict__ e_base, const double* __restrict__ e_coat, const double* __restrict__ xpow,
-                 const uint8_t* __restrict__ fixed_f, double* __restrict__ out) {
+                 const uint8_t* __restrict__ fixed_f, const double* __restrict__ child_g, double* __restrict__ out) {
     constexpr int S = 4 * ND, S2 = S * S;
     __shared__ double s_child[4][S2];  // one warp's child matrix at a time
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -101,6 +128,31 @@ coarsen_elements(int64_t nxf, int64_t nyf, int64_t nxc, int64_t nyc, const doubl
         double acc[NE];
 #pragma unroll
         for (int m = 0; m < NE; ++m) acc[m] = 0.0;
+        if (LEVEL0 && fullx && fully) {
+            // Fast path (all but the elements touching a Dirichlet node): the four children share one element
+            // matrix, so the parent is  sum_c x_c^p G_c  with the four precomputed images G_c = P_c^T Ke P_c.
+            uint32_t fm = 0u;
+            if (fixed_f && lane < 9) fm = fixed_f[(2 * J + lane / 3) * (nxf + 1) + 2 * I + lane % 3];
+            if (!__any_sync(0xffffffffu, fm != 0u)) {
+                double w[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) w[c] = xpow ? __ldg(&xpow[(2 * I + (c >> 1)) * nyf + 2 * J + (c & 1)]) : 1.0;
+                double* o = out + E * S2;
+#pragma unroll
+                for (int m = 0; m < NE; ++m) {
+                    const int idx = lane + 32 * m;
+                    if (idx < S2) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            v += e_coat ? __ldg(&child_g[c * S2 + idx]) + w[c] * __ldg(&child_g[(4 + c) * S2 + idx])
+                                        : w[c] * __ldg(&child_g[c * S2 + idx]);
+                        o[idx] = v;
+                    }
+                }
+                continue;
+            }
+        }
         for (int ca = 0; ca <= (fullx ? 1 : 0); ++ca)
             for (int cb = 0; cb <= (fully ? 1 : 0); ++cb) {
                 const int64_t ci = 2 * I + ca, cj = 2 * J + cb;
@@ -556,6 +608,7 @@ extern "C" int femol_gmg_destroy(femol_gmg* g) {
         cudaFree(L.dinv); cudaFree(L.t);
     }
     cudaFree(g->coarse_inv);
+    cudaFree(g->child_g);
     cudaFree(g->d_desc);
     delete g;
     return FEMOL_OK;
@@ -620,6 +673,7 @@ extern "C" int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t f
     }
     g->nc = CL.n;
     GCHECK(cudaMalloc(&g->coarse_inv, CL.n * CL.n * sizeof(double)));
+    GCHECK(cudaMalloc(&g->child_g, (size_t)2 * 4 * 16 * g->nd * g->nd * sizeof(double)));
     {   // descriptors for the fused single-CTA coarse V-cycle (levels with at most a few thousand nodes)
         LevelDesc h[GMG_MAX_LEVELS];
         memset(h, 0, sizeof(h));
@@ -657,11 +711,15 @@ extern "C" int femol_gmg_setup(femol_gmg* g, const double* e_base, const double*
         const int64_t cap = (int64_t)femol_sm_count() * 16;
         if (blocks > cap) blocks = cap;
         if (nd == 2) {
-            if (l == 1) coarsen_elements<2, true><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, nullptr, e_base, e_coat, xpow, F.fixed, C.ke);
-            else coarsen_elements<2, false><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, F.ke, nullptr, nullptr, nullptr, F.fixed, C.ke);
+            if (l == 1) {
+                child_images<2><<<2, 256, 0, st>>>(e_base, e_coat, g->child_g);
+                coarsen_elements<2, true><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, nullptr, e_base, e_coat, xpow, F.fixed, g->child_g, C.ke);
+            } else coarsen_elements<2, false><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, F.ke, nullptr, nullptr, nullptr, F.fixed, nullptr, C.ke);
         } else {
-            if (l == 1) coarsen_elements<6, true><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, nullptr, e_base, e_coat, xpow, F.fixed, C.ke);
-            else coarsen_elements<6, false><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, F.ke, nullptr, nullptr, nullptr, F.fixed, C.ke);
+            if (l == 1) {
+                child_images<6><<<18, 256, 0, st>>>(e_base, e_coat, g->child_g);
+                coarsen_elements<6, true><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, nullptr, e_base, e_coat, xpow, F.fixed, g->child_g, C.ke);
+            } else coarsen_elements<6, false><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, F.ke, nullptr, nullptr, nullptr, F.fixed, nullptr, C.ke);
         }
         FEMOL_LAUNCH_CHECK();
         int rc = femol_assemble(C.plan, C.ke, 1, nullptr, 0, nullptr, 1.0, C.fixed, nullptr, C.vals, st);

@@ -4,118 +4,235 @@
 // The assembled CSR K stays the product of femol_assemble (it is what `FEM_Problem.K` returns and what the
 // parity tests compare), but INSIDE the solvers every fine-level product K p costs 8*nnz + ... = 720 MB of HBM
 // traffic per launch on cfg 2, while the information content is one element matrix (512 B), one density per
-// element and the vector: 8*N_e + 16*n = 80 MB.  This kernel moves only that: one thread per node, the 3 x 3
-// node patch of u in registers, the element matrices broadcast from shared memory.  It is selected by the
+// element and the vector: 8*N_e + 16*n = 80 MB.  This kernel moves only that: a CTA per 32 x 16 node tile staged
+// in shared memory, one thread per node, the element matrix as constant-bank operands.  It is selected by the
 // solvers (femol_apply_launch) when the plan carries a matrix-free descriptor for the value array in use.
 #include "common.cuh"
 #include "spmv.cuh"
+#include <cstring>
+
+extern "C" int femol_dot(int64_t n, const double* a, const double* b, double* out, double* ws, void* stream);
 
 namespace {
 
+// Nodes are numbered x-fastest (n = j (nx+1) + i) but elements y-fastest (e = i ny + j, mesh.py:852-860), so a
+// thread-per-node sweep reads the densities with stride ny.  Each CTA therefore owns a TI x TJ tile of nodes and
+// stages what the tile needs through shared memory with both arrays read along their own fast axis:
+//   s_u  (TJ+2) x (TI+2) nodes of u, rows along i, fixed dofs already zeroed (columns of fixed dofs are 0 in K)
+//   s_w  (TI+1) x (TJ+1) element weights x^p, rows along j, 0 (coating: -1) outside the mesh
+//
+// The element matrix travels as a kernel parameter: every thread multiplies by the same entries, so they are
+// constant-bank operands of the DFMAs (measured on B200, tools/ubench/fp64_rate.cu: one broadcast LDS.128 per DFMA
+// caps the FP64 pipe at 9 of its 33.7 TFLOP/s; with constant operands the loop is the 64 (ND = 2) / 576 (ND = 6)
+// DFMAs per node and nothing else).
 template <int ND, bool COAT>
-__global__ void __launch_bounds__(128)
-stencil_apply_kernel(int64_t nx, int64_t ny, const double* __restrict__ e_base, const double* __restrict__ e_coat,
-                     const double* __restrict__ xpow, const uint8_t* __restrict__ fixed, const double* __restrict__ u,
-                     double* __restrict__ y, const double* __restrict__ dot_with, double* __restrict__ dot_out,
-                     double* __restrict__ red_ws) {
-    constexpr int S = 4 * ND, S2 = S * S;
-    extern __shared__ double s_k[];  // [S2] base | [S2] coat
+struct StencilMat {
+    double base[16 * ND * ND];
+    double coat[COAT ? 16 * ND * ND : 1];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// A CTA owns NT consecutive tiles.  It first issues the asynchronous copies (cp.async, zero-filled outside the
+// mesh) of all NT patches - NT x 15-19 KB in flight per CTA, which is what hides the DRAM latency: a version
+// with one tile per CTA and ordinary loads ran at 1.4 TB/s - then consumes them in order.  Everything is
+// straight-line (no loop around the multiply), so the element-matrix operands are read from the constant bank
+// where they are used instead of being hoisted into, and spilled from, registers.
+template <int ND, bool COAT, int TI, int TJ, int NT>
+__global__ void __launch_bounds__(TI * TJ, (ND == 2 || !COAT) ? 2 : 1)
+stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int ny, int tiles_i, int n_tiles, int cta0,
+                    const double* __restrict__ xpow, const uint8_t* __restrict__ fixed,
+                    const double* __restrict__ u, double* __restrict__ y, const double* __restrict__ dot_with,
+                    double* __restrict__ dot_out, double* __restrict__ red_ws) {
+    // 32-bit index arithmetic throughout (femol_plan_set_matrix_free checks n_dof < 2^31): the first version of
+    // this kernel spent more than half of its issue slots on 64-bit address computation
+    constexpr int S = 4 * ND, PI = TI + 2, PJ = TJ + 2, WI = TI + 1, WJ = TJ + 1, H = ND / 2, NTH = TI * TJ;
+    constexpr int STAGE = PJ * PI * ND + WI * WJ + ((WI * WJ) & 1);   // doubles per tile buffer, 16-byte multiple
+    constexpr int NPN = (PJ * PI + NTH - 1) / NTH;                    // patch nodes per thread (mask handling)
+    extern __shared__ __align__(16) double s_mem[];
     __shared__ double s_red[32];
-    for (int i = threadIdx.x; i < S2; i += blockDim.x) { s_k[i] = e_base[i]; if (COAT) s_k[S2 + i] = e_coat[i]; }
-    __syncthreads();
-    const int64_t npx = nx + 1, n_nodes = npx * (ny + 1);
-    double dot[1] = {0.0};
-    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < n_nodes; n += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = n / npx, i = n - j * npx;
-        // 3 x 3 patch of u with fixed dofs zeroed (columns of fixed dofs are zero in K)
-        double up[3][3][ND];
+    const int npx = nx + 1;
+    const int first = (cta0 + (int)blockIdx.x) * NT;
+    const int tj0 = first / tiles_i, ti0 = first - tj0 * tiles_i;
+    uint32_t fm[NT][NPN];
+    {
+        int ti = ti0, tj = tj0;
 #pragma unroll
-        for (int dj = 0; dj < 3; ++dj)
+        for (int k = 0; k < NT; ++k) {
+            if (first + k < n_tiles) {
+                const int i0 = ti * TI, j0 = tj * TJ;
+                double* s_u = s_mem + k * STAGE;          // [PJ][PI][ND]
+                double* s_w = s_u + PJ * PI * ND;         // [WI][WJ]
 #pragma unroll
-            for (int di = 0; di < 3; ++di) {
-                const int64_t ii = i + di - 1, jj = j + dj - 1;
-                const bool ok = ii >= 0 && ii <= nx && jj >= 0 && jj <= ny;
-                const int64_t m = jj * npx + ii;
-                const uint32_t fm = (ok && fixed) ? fixed[m] : 0u;
-#pragma unroll
-                for (int d = 0; d < ND; d += 2) {
-                    double2 v = ok ? __ldg(reinterpret_cast<const double2*>(u + m * ND + d)) : make_double2(0.0, 0.0);
-                    if ((fm >> d) & 1u) v.x = 0.0;
-                    if ((fm >> (d + 1)) & 1u) v.y = 0.0;
-                    up[dj][di][d] = v.x; up[dj][di][d + 1] = v.y;
-                }
-            }
-        double acc[ND];
-#pragma unroll
-        for (int d = 0; d < ND; ++d) acc[d] = 0.0;
-        // the four elements around node (i, j): element (ei, ej) = (i - 1 + ex, j - 1 + ey)
-#pragma unroll
-        for (int ey = 0; ey < 2; ++ey)
-#pragma unroll
-            for (int ex = 0; ex < 2; ++ex) {
-                const int64_t ei = i - 1 + ex, ej = j - 1 + ey;
-                if (ei < 0 || ei >= nx || ej < 0 || ej >= ny) continue;
-                const double w = xpow ? __ldg(&xpow[ei * ny + ej]) : 1.0;
-                // local index of node (i, j) in that element: Q4 order (0,0) (1,0) (1,1) (0,1)
-                const int lx = 1 - ex, ly = 1 - ey;
-                const int a = ly == 0 ? lx : 3 - lx;
-                double part[ND];
-#pragma unroll
-                for (int d = 0; d < ND; ++d) part[d] = 0.0;
-                double partc[ND];
-#pragma unroll
-                for (int d = 0; d < ND; ++d) partc[d] = 0.0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int bx = (b == 1 || b == 2) ? 1 : 0, by = (b >= 2) ? 1 : 0;
-                    const double* ub = up[ey + by][ex + bx];   // node (ei + bx, ej + by) in patch coordinates
-#pragma unroll
-                    for (int da = 0; da < ND; ++da) {
-                        const int row = (a * ND + da) * S + b * ND;
-#pragma unroll
-                        for (int db = 0; db < ND; ++db) {
-                            part[da] += s_k[row + db] * ub[db];
-                            if (COAT) partc[da] += s_k[S2 + row + db] * ub[db];
-                        }
-                    }
+                for (int it = threadIdx.x; it < PJ * PI * H; it += NTH) {
+                    const int r = it / (PI * H), c = it - r * (PI * H);
+                    const int ci = c / H, d = (c - ci * H) * 2;
+                    const int ii = i0 - 1 + ci, jj = j0 - 1 + r;
+                    const bool in = (unsigned)ii <= (unsigned)nx && (unsigned)jj <= (unsigned)ny;
+                    cp_async16(s_u + it * 2, u + (in ? (jj * npx + ii) * ND + d : 0), in ? 16 : 0);
                 }
 #pragma unroll
-                for (int d = 0; d < ND; ++d) acc[d] += COAT ? part[d] + w * partc[d] : w * part[d];
-            }
-        // rows of fixed dofs are the identity
-        const uint32_t fr = fixed ? fixed[n] : 0u;
+                for (int it = threadIdx.x; it < WI * WJ; it += NTH) {
+                    const int ri = it / WJ, rj = it - ri * WJ;
+                    const int ei = i0 - 1 + ri, ej = j0 - 1 + rj;
+                    const bool in = (unsigned)ei < (unsigned)nx && (unsigned)ej < (unsigned)ny;
+                    if (xpow) cp_async8(s_w + it, xpow + (in ? ei * ny + ej : 0), in ? 8 : 0);
+                    else s_w[it] = in ? 1.0 : 0.0;
+                }
 #pragma unroll
-        for (int d = 0; d < ND; d += 2) {
-            double2 o = make_double2(acc[d], acc[d + 1]);
-            if (fr) {
-                const double2 orig = __ldg(reinterpret_cast<const double2*>(u + n * ND + d));
-                if ((fr >> d) & 1u) o.x = orig.x;
-                if ((fr >> (d + 1)) & 1u) o.y = orig.y;
+                for (int q = 0; q < NPN; ++q) {
+                    const int pn = threadIdx.x + q * NTH;
+                    const int r = pn / PI, ci = pn - r * PI;
+                    const int ii = i0 - 1 + ci, jj = j0 - 1 + r;
+                    fm[k][q] = (fixed && pn < PJ * PI && (unsigned)ii <= (unsigned)nx && (unsigned)jj <= (unsigned)ny)
+                                   ? __ldg(&fixed[jj * npx + ii]) : 0u;
+                }
             }
-            *reinterpret_cast<double2*>(y + n * ND + d) = o;
-            if (dot_with) dot[0] += o.x * dot_with[n * ND + d] + o.y * dot_with[n * ND + d + 1];
+            cp_async_commit();
+            if (++ti == tiles_i) { ti = 0; ++tj; }
         }
     }
+    double dot[1] = {0.0};
+    const int lj = threadIdx.x / TI, li = threadIdx.x - lj * TI;
+    int ti = ti0, tj = tj0;
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+        if (first + k >= n_tiles) break;     // uniform across the CTA
+        if (k == 0) cp_async_wait<NT - 1>();
+        else if (k == 1) cp_async_wait<(NT > 2 ? NT - 2 : 0)>();
+        else if (k == 2) cp_async_wait<(NT > 3 ? NT - 3 : 0)>();
+        else cp_async_wait<0>();
+        double* s_u = s_mem + k * STAGE;
+        const double* s_w = s_u + PJ * PI * ND;
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int q = 0; q < NPN; ++q) mine |= fm[k][q];
+        if (__syncthreads_or(mine != 0u)) {
+            // columns of fixed dofs are zero in K: clear them in the staged patch (rare: Dirichlet boundary tiles)
+#pragma unroll
+            for (int q = 0; q < NPN; ++q)
+                if (fm[k][q]) {
+                    const int pn = threadIdx.x + q * NTH;
+#pragma unroll
+                    for (int d = 0; d < ND; ++d)
+                        if ((fm[k][q] >> d) & 1u) s_u[pn * ND + d] = 0.0;
+                }
+            __syncthreads();
+        }
+        const int i = ti * TI + li, j = tj * TJ + lj;
+        if (++ti == tiles_i) { ti = 0; ++tj; }
+        if (i <= nx && j <= ny) {
+            const int n = j * npx + i;
+            double acc[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) acc[d] = 0.0;
+            // the four elements around node (i, j): element (i - 1 + ex, j - 1 + ey) = tile element (li + ex, lj + ey)
+#pragma unroll
+            for (int ey = 0; ey < 2; ++ey)
+#pragma unroll
+                for (int ex = 0; ex < 2; ++ex) {
+                    const double w = s_w[(li + ex) * WJ + lj + ey];
+                    // local index of node (i, j) in that element: Q4 order (0,0) (1,0) (1,1) (0,1)
+                    const int lx = 1 - ex, ly = 1 - ey;
+                    const int a = ly == 0 ? lx : 3 - lx;
+                    double part[ND], partc[ND];
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) { part[d] = 0.0; partc[d] = 0.0; }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int bx = (b == 1 || b == 2) ? 1 : 0, by = (b >= 2) ? 1 : 0;
+                        double ub[ND];                              // node (ei + bx, ej + by) of the staged patch
+#pragma unroll
+                        for (int d = 0; d < ND; d += 2) {
+                            const double2 v = *reinterpret_cast<const double2*>(s_u + ((lj + ey + by) * PI + li + ex + bx) * ND + d);
+                            ub[d] = v.x; ub[d + 1] = v.y;
+                        }
+#pragma unroll
+                        for (int da = 0; da < ND; ++da) {
+                            const int row = (a * ND + da) * S + b * ND;
+#pragma unroll
+                            for (int db = 0; db < ND; ++db) {
+                                part[da] = fma(km.base[row + db], ub[db], part[da]);
+                                if (COAT) partc[da] = fma(km.coat[row + db], ub[db], partc[da]);
+                            }
+                        }
+                    }
+                    // outside the mesh w is 0 (zero fill); the coating's base part is unweighted, so test explicitly
+                    const bool inside = (unsigned)(i - 1 + ex) < (unsigned)nx && (unsigned)(j - 1 + ey) < (unsigned)ny;
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) acc[d] += COAT ? (inside ? fma(w, partc[d], part[d]) : 0.0) : w * part[d];
+                }
+            // rows of fixed dofs are the identity
+            const uint32_t frow = fixed ? __ldg(&fixed[n]) : 0u;
+            const double* un = u + (size_t)n * ND;
+            double* yn = y + (size_t)n * ND;
+#pragma unroll
+            for (int d = 0; d < ND; d += 2) {
+                double2 o = make_double2(acc[d], acc[d + 1]);
+                if (frow) {
+                    const double2 orig = __ldg(reinterpret_cast<const double2*>(un + d));
+                    if ((frow >> d) & 1u) o.x = orig.x;
+                    if ((frow >> (d + 1)) & 1u) o.y = orig.y;
+                }
+                *reinterpret_cast<double2*>(yn + d) = o;
+                if (dot_with) {
+                    const double2 q = __ldg(reinterpret_cast<const double2*>(dot_with + (size_t)n * ND + d));
+                    dot[0] += o.x * q.x + o.y * q.y;
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
     if (dot_out) grid_sum_finish<1>(dot, red_ws, red_ticket(red_ws), dot_out, s_red);
 }
 
-template <int ND>
-int launch_stencil(const femol_matrix_free* mf, int sm_count, const double* x, double* y, const double* dot_with,
-                   double* dot_out, double* red_ws, cudaStream_t st) {
-    const int64_t n_nodes = (mf->nx + 1) * (mf->ny + 1);
-    int64_t blocks = (n_nodes + 127) / 128;
-    int64_t cap = (int64_t)sm_count * 12;
-    if (cap > FEMOL_RED_MAX_BLOCKS) cap = FEMOL_RED_MAX_BLOCKS;
-    if (blocks > cap) blocks = cap;
-    const size_t smem = (size_t)(mf->e_coat ? 2 : 1) * 16 * ND * ND * sizeof(double);
-    if (mf->e_coat)
-        stencil_apply_kernel<ND, true><<<(int)blocks, 128, smem, st>>>(mf->nx, mf->ny, mf->e_base, mf->e_coat, mf->xpow,
-                                                                       mf->fixed, x, y, dot_with, dot_out, red_ws);
-    else
-        stencil_apply_kernel<ND, false><<<(int)blocks, 128, smem, st>>>(mf->nx, mf->ny, mf->e_base, nullptr, mf->xpow,
-                                                                        mf->fixed, x, y, dot_with, dot_out, red_ws);
-    FEMOL_LAUNCH_CHECK();
+template <int ND, bool COAT>
+int launch_stencil_c(femol_plan_t p, const femol_matrix_free* mf, const double* x, double* y, const double* dot_with,
+                     double* dot_out, double* red_ws, cudaStream_t st) {
+    constexpr int TI = 32, TJ = ND == 2 ? 16 : 8, NT = 4;
+    constexpr int WW = (TI + 1) * (TJ + 1);
+    constexpr size_t smem = (size_t)NT * ((TJ + 2) * (TI + 2) * ND + WW + (WW & 1)) * sizeof(double);
+    static bool configured = false;
+    auto kern = stencil_tile_kernel<ND, COAT, TI, TJ, NT>;
+    if (!configured) {
+        FEMOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int tiles_i = (int)((mf->nx + 1 + TI - 1) / TI);
+    const int64_t n_tiles = (int64_t)tiles_i * ((mf->ny + 1 + TJ - 1) / TJ);
+    const int64_t n_cta = (n_tiles + NT - 1) / NT;
+    StencilMat<ND, COAT> km;
+    memcpy(km.base, mf->e_base, sizeof(km.base));
+    if (COAT) memcpy(km.coat, mf->e_coat, sizeof(km.coat));
+    // the one-channel grid sum has FEMOL_RED_CHANNELS * FEMOL_RED_MAX_BLOCKS slots; larger grids go in chunks and
+    // the dot product becomes its own pass
+    const int64_t max_grid = (int64_t)FEMOL_RED_CHANNELS * FEMOL_RED_MAX_BLOCKS;
+    const bool fused = n_cta <= max_grid;
+    for (int64_t c0 = 0; c0 < n_cta; c0 += max_grid) {
+        const int64_t nb = n_cta - c0 < max_grid ? n_cta - c0 : max_grid;
+        kern<<<(int)nb, TI * TJ, smem, st>>>(km, (int)mf->nx, (int)mf->ny, tiles_i, (int)n_tiles, (int)c0, mf->xpow, mf->fixed, x, y,
+                                             fused ? dot_with : nullptr, fused ? dot_out : nullptr, red_ws);
+        FEMOL_LAUNCH_CHECK();
+    }
+    if (!fused && dot_out) return femol_dot(p->n_nodes * p->ndof, y, dot_with, dot_out, red_ws, st);
     return FEMOL_OK;
+}
+
+template <int ND>
+int launch_stencil(femol_plan_t p, const femol_matrix_free* mf, const double* x, double* y, const double* dot_with,
+                   double* dot_out, double* red_ws, cudaStream_t st) {
+    return mf->has_coat ? launch_stencil_c<ND, true>(p, mf, x, y, dot_with, dot_out, red_ws, st)
+                        : launch_stencil_c<ND, false>(p, mf, x, y, dot_with, dot_out, red_ws, st);
 }
 
 }  // namespace
@@ -126,8 +243,8 @@ int femol_apply_launch(femol_plan_t p, const double* vals, const double* x, doub
                        double* dot_out, double* red_ws, cudaStream_t st) {
     const femol_matrix_free* mf = p->mf;
     if (mf && mf->vals == vals) {
-        if (p->ndof == 2) return launch_stencil<2>(mf, p->sm_count, x, y, dot_with, dot_out, red_ws, st);
-        if (p->ndof == 6) return launch_stencil<6>(mf, p->sm_count, x, y, dot_with, dot_out, red_ws, st);
+        if (p->ndof == 2) return launch_stencil<2>(p, mf, x, y, dot_with, dot_out, red_ws, st);
+        if (p->ndof == 6) return launch_stencil<6>(p, mf, x, y, dot_with, dot_out, red_ws, st);
     }
     return femol_spmv_launch(p, vals, x, y, dot_with, dot_out, red_ws, st);
 }
@@ -143,9 +260,13 @@ extern "C" int femol_plan_set_matrix_free(femol_plan_t p, int64_t nx, int64_t ny
     }
     FEMOL_REQUIRE(p->nn == 4 && (p->ndof == 2 || p->ndof == 6) && p->n_elem == nx * ny && p->n_nodes == (nx + 1) * (ny + 1),
                   "femol_plan_set_matrix_free: plan is not an nx x ny structured Q4 mesh");
+    FEMOL_REQUIRE(p->n_nodes * p->ndof < (int64_t)2147483647, "femol_plan_set_matrix_free: more than 2^31 dofs");
     if (!p->mf) p->mf = new femol_matrix_free();
-    p->mf->nx = nx; p->mf->ny = ny; p->mf->e_base = e_base; p->mf->e_coat = e_coat; p->mf->xpow = xpow;
-    p->mf->fixed = fixed; p->mf->vals = vals;
+    const size_t s2 = (size_t)16 * p->ndof * p->ndof;
+    p->mf->nx = nx; p->mf->ny = ny; p->mf->xpow = xpow; p->mf->fixed = fixed; p->mf->vals = vals;
+    memcpy(p->mf->e_base, e_base, s2 * sizeof(double));
+    p->mf->has_coat = e_coat != nullptr;
+    if (e_coat) memcpy(p->mf->e_coat, e_coat, s2 * sizeof(double));
     return FEMOL_OK;
 }
 

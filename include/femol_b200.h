@@ -109,11 +109,12 @@ int femol_spmv_csr(int64_t n_rows, const int32_t* indptr, const int32_t* indices
 /* Matrix-free K for the solvers on structured rectangle_Q4 meshes (nodes x-fastest, element e = i*ny + j):
  * declares that the value array `vals` equals sum_e (xpow_e * e_base [or e_base + xpow_e * e_coat]) with the
  * Dirichlet mask `fixed` applied — i.e. the arguments of the femol_assemble call that produced it.  femol_pcg /
- * femol_pcg_gmg then apply K from these 80 MB instead of streaming the 720 MB of CSR values (cfg 2).  Pointers
- * are borrowed and must outlive the solves; pass e_base = NULL to clear.  femol_apply = K x through the operator
- * the solvers use (femol_spmv always uses the CSR values). */
-int femol_plan_set_matrix_free(femol_plan_t plan, int64_t nx, int64_t ny, const double* e_base,
-                               const double* e_coat, const double* xpow, const uint8_t* fixed, const double* vals);
+ * femol_pcg_gmg then apply K from these 80 MB instead of streaming the 720 MB of CSR values (cfg 2).
+ * e_base_host / e_coat_host: the shared (4 ndof)^2 element matrices in HOST memory (copied; they become kernel
+ * parameters).  xpow, fixed, vals: device pointers, borrowed, must outlive the solves.  e_base_host = NULL clears.
+ * femol_apply = K x through the operator the solvers use (femol_spmv always uses the CSR values). */
+int femol_plan_set_matrix_free(femol_plan_t plan, int64_t nx, int64_t ny, const double* e_base_host,
+                               const double* e_coat_host, const double* xpow, const uint8_t* fixed, const double* vals);
 int femol_apply(femol_plan_t plan, const double* vals, const double* x, double* y, void* stream);
 
 /* ---- K5: preconditioned conjugate gradients (replaces spsolve, FEM.py:258-265) --------------
