@@ -217,7 +217,8 @@ coarsen_elements(int64_t nxf, int64_t nyf, int64_t nxc, int64_t nyc, const doubl
 template <int ND>
 __global__ void __launch_bounds__(256)
 restrict_kernel(int64_t nxf, int64_t nyf, int64_t nxc, int64_t nyc, const uint8_t* __restrict__ ff,
-                const uint8_t* __restrict__ fc, const double* __restrict__ rf, double* __restrict__ rc) {
+                const uint8_t* __restrict__ fc, const double* __restrict__ rf, double* __restrict__ rc,
+                const double* __restrict__ dinv_c, double omega, double* __restrict__ ec) {
     const int64_t nn = (nxc + 1) * (nyc + 1);
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nn; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t J = t / (nxc + 1), I = t - J * (nxc + 1);
@@ -249,15 +250,28 @@ restrict_kernel(int64_t nxf, int64_t nyf, int64_t nxc, int64_t nyc, const uint8_
         }
         const uint32_t cm = fc ? fc[t] : 0u;
 #pragma unroll
-        for (int d = 0; d < ND; ++d) rc[t * ND + d] = ((cm >> d) & 1u) ? 0.0 : acc[d];
+        for (int d = 0; d < ND; ++d) {
+            if ((cm >> d) & 1u) acc[d] = 0.0;
+            rc[t * ND + d] = acc[d];
+        }
+        if (dinv_c) {   // the coarse level's first smoothing sweep from a zero guess: e_c = omega Dinv r_c
+            const double* B = dinv_c + t * ND * ND;
+#pragma unroll
+            for (int a = 0; a < ND; ++a) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int b = 0; b < ND; ++b) sacc += __ldg(&B[a * ND + b]) * acc[b];
+                ec[t * ND + a] = omega * sacc;
+            }
+        }
     }
 }
 
-// e_f += P e_c   (fixed fine dofs untouched)
+// out = e_f + P e_c   (fixed fine dofs copied; out may alias e_f)
 template <int ND>
 __global__ void __launch_bounds__(256)
 prolong_add_kernel(int64_t nxf, int64_t nyf, int64_t nxc, const uint8_t* __restrict__ ff,
-                   const double* __restrict__ ec, double* __restrict__ ef) {
+                   const double* __restrict__ ec, const double* ef, double* out) {
     const int64_t nn = (nxf + 1) * (nyf + 1);
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nn; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t j = t / (nxf + 1), i = t - j * (nxf + 1);
@@ -268,11 +282,13 @@ prolong_add_kernel(int64_t nxf, int64_t nyf, int64_t nxc, const uint8_t* __restr
         const int64_t c00 = J0 * (nxc + 1) + I0, c10 = J0 * (nxc + 1) + I1, c01 = J1 * (nxc + 1) + I0, c11 = J1 * (nxc + 1) + I1;
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
-            if ((fm >> d) & 1u) continue;
-            double v = u0 * v0 * ec[c00 * ND + d];
-            if (u1 != 0.0) v += u1 * v0 * ec[c10 * ND + d];
-            if (v1 != 0.0) { v += u0 * v1 * ec[c01 * ND + d]; if (u1 != 0.0) v += u1 * v1 * ec[c11 * ND + d]; }
-            ef[t * ND + d] += v;
+            double v = 0.0;
+            if (!((fm >> d) & 1u)) {
+                v = u0 * v0 * ec[c00 * ND + d];
+                if (u1 != 0.0) v += u1 * v0 * ec[c10 * ND + d];
+                if (v1 != 0.0) { v += u0 * v1 * ec[c01 * ND + d]; if (u1 != 0.0) v += u1 * v1 * ec[c11 * ND + d]; }
+            }
+            out[t * ND + d] = ef[t * ND + d] + v;
         }
     }
 }
@@ -472,10 +488,12 @@ __device__ void cta_prolong_add(const LevelDesc& F, const LevelDesc& C, const do
         const int64_t c00 = J0 * (C.nx + 1) + I0, c10 = J0 * (C.nx + 1) + I1, c01 = J1 * (C.nx + 1) + I0, c11 = J1 * (C.nx + 1) + I1;
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
-            if ((fm >> d) & 1u) continue;
-            double v = u0 * v0 * ec[c00 * ND + d];
-            if (u1 != 0.0) v += u1 * v0 * ec[c10 * ND + d];
-            if (v1 != 0.0) { v += u0 * v1 * ec[c01 * ND + d]; if (u1 != 0.0) v += u1 * v1 * ec[c11 * ND + d]; }
+            double v = 0.0;
+            if (!((fm >> d) & 1u)) {
+                v = u0 * v0 * ec[c00 * ND + d];
+                if (u1 != 0.0) v += u1 * v0 * ec[c10 * ND + d];
+                if (v1 != 0.0) { v += u0 * v1 * ec[c01 * ND + d]; if (u1 != 0.0) v += u1 * v1 * ec[c11 * ND + d]; }
+            }
             ef[t * ND + d] += v;
         }
     }
@@ -562,8 +580,9 @@ int smooth(femol_gmg* g, int l, const double* r, double* e, bool zero_start, cud
     return FEMOL_OK;
 }
 
+// `presmoothed`: e already holds the first sweep omega Dinv r (written by the restriction that produced r)
 template <int ND>
-int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st) {
+int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, bool presmoothed = false) {
     Level& L = g->lv[l];
     if (l >= 1 && l >= g->fused_from && g->d_desc) {
         coarse_vcycle_kernel<ND><<<1, 1024, 0, st>>>((const LevelDesc*)g->d_desc, l, g->n_levels - 1, g->nu, g->omega, g->coarse_inv, r, e);
@@ -576,17 +595,49 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st) {
         return FEMOL_OK;
     }
     Level& C = g->lv[l + 1];
-    int rc = smooth<ND>(g, l, r, e, true, st);
+    int rc;
+    if (g->nu == 1) {
+        // One pre- and one post-sweep with everything fused into the products (5 launches per level, was 7):
+        //   e = omega Dinv r                     (level 0: jacobi kernel; below: epilogue of the restriction)
+        //   t = r - K e                          (product, residual epilogue)
+        //   r_c = P^T t, e_c = omega Dinv_c r_c  (restriction)
+        //   ... coarse correction ...
+        //   t = e + P e_c                        (prolongation, out of place)
+        //   e = t + omega Dinv (r - K t)         (product, Jacobi epilogue)
+        if (!presmoothed) {
+            jacobi_kernel<ND, true><<<grid_for(L.n_nodes), 256, 0, st>>>(L.n_nodes, g->omega, L.dinv, r, nullptr, e);
+            FEMOL_LAUNCH_CHECK();
+        }
+        const femol_epilogue res = {FEMOL_EPI_RESIDUAL, r, nullptr, 0.0};
+        rc = femol_apply_epilogue_launch(L.plan, L.vals, e, L.t, res, st);
+        if (rc != FEMOL_OK) return rc;
+        const bool coarse_regular = !(l + 1 >= g->fused_from && g->d_desc) && (l + 1 != g->n_levels - 1);
+        restrict_kernel<ND><<<grid_for(C.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, C.ny, L.fixed, C.fixed, L.t, C.r,
+                                                                 coarse_regular ? C.dinv : nullptr, g->omega, C.e);
+        FEMOL_LAUNCH_CHECK();
+        rc = vcycle<ND>(g, l + 1, C.r, C.e, st, coarse_regular);
+        if (rc != FEMOL_OK) return rc;
+        if (femol_apply_has_jacobi(L.plan, L.vals)) {
+            prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e, L.t);
+            FEMOL_LAUNCH_CHECK();
+            const femol_epilogue jac = {FEMOL_EPI_JACOBI, r, L.dinv, g->omega};
+            return femol_apply_epilogue_launch(L.plan, L.vals, L.t, e, jac, st);
+        }
+        prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e, e);
+        FEMOL_LAUNCH_CHECK();
+        return smooth<ND>(g, l, r, e, false, st);
+    }
+    rc = smooth<ND>(g, l, r, e, true, st);
     if (rc != FEMOL_OK) return rc;
     rc = femol_apply_launch(L.plan, L.vals, e, L.t, nullptr, nullptr, nullptr, st);
     if (rc != FEMOL_OK) return rc;
     residual_kernel<<<grid_for(L.n), 256, 0, st>>>(L.n, r, L.t, L.t);
     FEMOL_LAUNCH_CHECK();
-    restrict_kernel<ND><<<grid_for(C.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, C.ny, L.fixed, C.fixed, L.t, C.r);
+    restrict_kernel<ND><<<grid_for(C.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, C.ny, L.fixed, C.fixed, L.t, C.r, nullptr, 0.0, nullptr);
     FEMOL_LAUNCH_CHECK();
     rc = vcycle<ND>(g, l + 1, C.r, C.e, st);
     if (rc != FEMOL_OK) return rc;
-    prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e);
+    prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e, e);
     FEMOL_LAUNCH_CHECK();
     return smooth<ND>(g, l, r, e, false, st);
 }

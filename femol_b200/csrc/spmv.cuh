@@ -9,11 +9,15 @@ size_t femol_l2_persist_bytes();
 // streaming (evict-first) loads so that the L2 stays available for the gathered x vector; x is read
 // through the read-only path as double2 (two dofs of one neighbour node per load).
 // Optional fused dot product: dot_out[0] = sum_r y[r] * dot_with[r] (deterministic grid reduction).
-template <int ND, int G>
+// MODE (femol_epilogue): 0  y = K x;  1  y = rhs - K x;  2  y = x + omega Dinv (rhs - K x)  (ND = 2 only: the two
+// rows of a node sit in neighbouring lane groups of one warp, so the 2 x 2 block product is one shuffle away).
+template <int ND, int G, int MODE = 0>
 __global__ void __launch_bounds__(256)
 spmv_node_kernel(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx,
                  const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
-                 const double* __restrict__ dot_with, double* __restrict__ dot_out, double* __restrict__ red_ws) {
+                 const double* __restrict__ dot_with, double* __restrict__ dot_out, double* __restrict__ red_ws,
+                 const double* __restrict__ rhs = nullptr, const double* __restrict__ dinv = nullptr, double omega = 0.0) {
+    static_assert(MODE != 2 || (ND == 2 && 32 % (2 * G) == 0), "fused Jacobi needs both rows of a node in one warp");
     static_assert(ND % 2 == 0, "ndof must be even for the double2 path");
     constexpr int H = ND / 2;  // double2 pairs per neighbour node
     __shared__ double s_red[32];
@@ -46,9 +50,19 @@ spmv_node_kernel(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, const int
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (g == 0 && r < n_rows) {
-            y[r] = acc;
-            if (dot_with) dot[0] += acc * dot_with[r];
+        if (MODE == 2) {
+            const double other = __shfl_xor_sync(0xffffffffu, acc, G);   // K x of the node's other dof
+            if (g == 0 && r < n_rows) {
+                const int64_t i = r >> 1;
+                const int da = (int)(r & 1);
+                const double mine = __ldg(&rhs[r]) - acc, theirs = __ldg(&rhs[r ^ 1]) - other;
+                const double2 d = __ldg(reinterpret_cast<const double2*>(dinv) + i * 2 + da);   // row da of the 2 x 2 block
+                y[r] = __ldg(&x[r]) + omega * (da == 0 ? d.x * mine + d.y * theirs : d.x * theirs + d.y * mine);
+            }
+        } else if (g == 0 && r < n_rows) {
+            const double out = MODE == 1 ? __ldg(&rhs[r]) - acc : acc;
+            y[r] = out;
+            if (dot_with) dot[0] += out * dot_with[r];
         }
     }
     if (dot_out) {
@@ -57,9 +71,10 @@ spmv_node_kernel(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, const int
     }
 }
 
-template <int ND>
+template <int ND, int MODE = 0>
 int spmv_node_launch(femol_plan_t p, const double* vals, const double* x, double* y, const double* dot_with,
-                     double* dot_out, double* red_ws, cudaStream_t st) {
+                     double* dot_out, double* red_ws, cudaStream_t st, const double* rhs = nullptr,
+                     const double* dinv = nullptr, double omega = 0.0) {
     constexpr int G = ND == 2 ? 4 : 8;
     const int64_t n_rows = p->n_nodes * ND;
     int64_t blocks = (n_rows * G + 255) / 256;
@@ -84,13 +99,14 @@ int spmv_node_launch(femol_plan_t p, const double* vals, const double* x, double
         attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cfg.attrs = attr; cfg.numAttrs = 1;
         const int64_t nn = p->n_nodes;
-        FEMOL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, spmv_node_kernel<ND, G>, nn, (const int32_t*)p->adj_ptr,
-                                            (const int32_t*)p->adj_idx, vals, x, y, dot_with, dot_out, red_ws));
+        FEMOL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, spmv_node_kernel<ND, G, MODE>, nn, (const int32_t*)p->adj_ptr,
+                                            (const int32_t*)p->adj_idx, vals, x, y, dot_with, dot_out, red_ws, rhs, dinv,
+                                            omega));
         femol_count_launch();
         return FEMOL_OK;
     }
-    spmv_node_kernel<ND, G><<<(int)blocks, 256, 0, st>>>(p->n_nodes, p->adj_ptr, p->adj_idx, vals, x, y, dot_with,
-                                                          dot_out, red_ws);
+    spmv_node_kernel<ND, G, MODE><<<(int)blocks, 256, 0, st>>>(p->n_nodes, p->adj_ptr, p->adj_idx, vals, x, y, dot_with,
+                                                                dot_out, red_ws, rhs, dinv, omega);
     FEMOL_LAUNCH_CHECK();
     return FEMOL_OK;
 }
@@ -100,3 +116,17 @@ int femol_spmv_launch(femol_plan_t p, const double* vals, const double* x, doubl
 // solver-side K x: matrix-free stencil when available for `vals` (stencil.cu), else the CSR kernel above
 int femol_apply_launch(femol_plan_t p, const double* vals, const double* x, double* y, const double* dot_with,
                        double* dot_out, double* red_ws, cudaStream_t st);
+// the same product with a fused epilogue (multigrid smoother / residual); y must not alias x
+struct femol_epilogue {
+    int mode;            // FEMOL_EPI_*
+    const double* rhs;   // r in modes 1, 2
+    const double* dinv;  // [n_nodes][ND][ND] block-diagonal inverse, mode 2
+    double omega;        // damping, mode 2
+};
+#define FEMOL_EPI_NONE 0      // y = K x
+#define FEMOL_EPI_RESIDUAL 1  // y = rhs - K x
+#define FEMOL_EPI_JACOBI 2    // y = x + omega Dinv (rhs - K x)
+// whether mode 2 is available for this (plan, vals): every ND on the stencil path, ND = 2 on the CSR path
+bool femol_apply_has_jacobi(femol_plan_t p, const double* vals);
+int femol_apply_epilogue_launch(femol_plan_t p, const double* vals, const double* x, double* y, const femol_epilogue& ep,
+                                cudaStream_t st);

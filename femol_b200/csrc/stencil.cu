@@ -48,12 +48,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // with one tile per CTA and ordinary loads ran at 1.4 TB/s - then consumes them in order.  Everything is
 // straight-line (no loop around the multiply), so the element-matrix operands are read from the constant bank
 // where they are used instead of being hoisted into, and spilled from, registers.
-template <int ND, bool COAT, int TI, int TJ, int NT>
+template <int ND, bool COAT, int TI, int TJ, int NT, int MODE>
 __global__ void __launch_bounds__(TI * TJ, (ND == 2 || !COAT) ? 2 : 1)
 stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int ny, int tiles_i, int n_tiles, int cta0,
                     const double* __restrict__ xpow, const uint8_t* __restrict__ fixed,
                     const double* __restrict__ u, double* __restrict__ y, const double* __restrict__ dot_with,
-                    double* __restrict__ dot_out, double* __restrict__ red_ws) {
+                    double* __restrict__ dot_out, double* __restrict__ red_ws, const double* __restrict__ rhs,
+                    const double* __restrict__ dinv, double omega) {
     // 32-bit index arithmetic throughout (femol_plan_set_matrix_free checks n_dof < 2^31): the first version of
     // this kernel spent more than half of its issue slots on 64-bit address computation
     constexpr int S = 4 * ND, PI = TI + 2, PJ = TJ + 2, WI = TI + 1, WJ = TJ + 1, H = ND / 2, NTH = TI * TJ;
@@ -176,16 +177,41 @@ stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int
             const uint32_t frow = fixed ? __ldg(&fixed[n]) : 0u;
             const double* un = u + (size_t)n * ND;
             double* yn = y + (size_t)n * ND;
+            if (frow) {
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                    if ((frow >> d) & 1u) acc[d] = __ldg(un + d);
+            }
+            if (MODE == 1) {            // y = rhs - K u
+#pragma unroll
+                for (int d = 0; d < ND; d += 2) {
+                    const double2 q = __ldg(reinterpret_cast<const double2*>(rhs + (size_t)n * ND + d));
+                    acc[d] = q.x - acc[d]; acc[d + 1] = q.y - acc[d + 1];
+                }
+            } else if (MODE == 2) {     // y = u + omega Dinv (rhs - K u)
+                double res[ND];
+#pragma unroll
+                for (int d = 0; d < ND; d += 2) {
+                    const double2 q = __ldg(reinterpret_cast<const double2*>(rhs + (size_t)n * ND + d));
+                    res[d] = q.x - acc[d]; res[d + 1] = q.y - acc[d + 1];
+                }
+                const double* B = dinv + (size_t)n * ND * ND;
+#pragma unroll
+                for (int da = 0; da < ND; ++da) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int db = 0; db < ND; db += 2) {
+                        const double2 b2 = __ldg(reinterpret_cast<const double2*>(B + da * ND + db));
+                        t = fma(b2.x, res[db], t); t = fma(b2.y, res[db + 1], t);
+                    }
+                    acc[da] = __ldg(un + da) + omega * t;
+                }
+            }
 #pragma unroll
             for (int d = 0; d < ND; d += 2) {
-                double2 o = make_double2(acc[d], acc[d + 1]);
-                if (frow) {
-                    const double2 orig = __ldg(reinterpret_cast<const double2*>(un + d));
-                    if ((frow >> d) & 1u) o.x = orig.x;
-                    if ((frow >> (d + 1)) & 1u) o.y = orig.y;
-                }
+                const double2 o = make_double2(acc[d], acc[d + 1]);
                 *reinterpret_cast<double2*>(yn + d) = o;
-                if (dot_with) {
+                if (MODE == 0 && dot_with) {
                     const double2 q = __ldg(reinterpret_cast<const double2*>(dot_with + (size_t)n * ND + d));
                     dot[0] += o.x * q.x + o.y * q.y;
                 }
@@ -196,14 +222,14 @@ stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int
     if (dot_out) grid_sum_finish<1>(dot, red_ws, red_ticket(red_ws), dot_out, s_red);
 }
 
-template <int ND, bool COAT>
+template <int ND, bool COAT, int MODE>
 int launch_stencil_c(femol_plan_t p, const femol_matrix_free* mf, const double* x, double* y, const double* dot_with,
-                     double* dot_out, double* red_ws, cudaStream_t st) {
+                     double* dot_out, double* red_ws, const femol_epilogue& ep, cudaStream_t st) {
     constexpr int TI = 32, TJ = ND == 2 ? 16 : 8, NT = 4;
     constexpr int WW = (TI + 1) * (TJ + 1);
     constexpr size_t smem = (size_t)NT * ((TJ + 2) * (TI + 2) * ND + WW + (WW & 1)) * sizeof(double);
     static bool configured = false;
-    auto kern = stencil_tile_kernel<ND, COAT, TI, TJ, NT>;
+    auto kern = stencil_tile_kernel<ND, COAT, TI, TJ, NT, MODE>;
     if (!configured) {
         FEMOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
@@ -221,32 +247,65 @@ int launch_stencil_c(femol_plan_t p, const femol_matrix_free* mf, const double* 
     for (int64_t c0 = 0; c0 < n_cta; c0 += max_grid) {
         const int64_t nb = n_cta - c0 < max_grid ? n_cta - c0 : max_grid;
         kern<<<(int)nb, TI * TJ, smem, st>>>(km, (int)mf->nx, (int)mf->ny, tiles_i, (int)n_tiles, (int)c0, mf->xpow, mf->fixed, x, y,
-                                             fused ? dot_with : nullptr, fused ? dot_out : nullptr, red_ws);
+                                             fused ? dot_with : nullptr, fused ? dot_out : nullptr, red_ws, ep.rhs, ep.dinv,
+                                             ep.omega);
         FEMOL_LAUNCH_CHECK();
     }
     if (!fused && dot_out) return femol_dot(p->n_nodes * p->ndof, y, dot_with, dot_out, red_ws, st);
     return FEMOL_OK;
 }
 
-template <int ND>
+template <int ND, int MODE>
 int launch_stencil(femol_plan_t p, const femol_matrix_free* mf, const double* x, double* y, const double* dot_with,
-                   double* dot_out, double* red_ws, cudaStream_t st) {
-    return mf->has_coat ? launch_stencil_c<ND, true>(p, mf, x, y, dot_with, dot_out, red_ws, st)
-                        : launch_stencil_c<ND, false>(p, mf, x, y, dot_with, dot_out, red_ws, st);
+                   double* dot_out, double* red_ws, const femol_epilogue& ep, cudaStream_t st) {
+    return mf->has_coat ? launch_stencil_c<ND, true, MODE>(p, mf, x, y, dot_with, dot_out, red_ws, ep, st)
+                        : launch_stencil_c<ND, false, MODE>(p, mf, x, y, dot_with, dot_out, red_ws, ep, st);
+}
+
+template <int ND>
+int launch_stencil_mode(femol_plan_t p, const femol_matrix_free* mf, const double* x, double* y, const double* dot_with,
+                        double* dot_out, double* red_ws, const femol_epilogue& ep, cudaStream_t st) {
+    if (ep.mode == FEMOL_EPI_RESIDUAL) return launch_stencil<ND, 1>(p, mf, x, y, nullptr, nullptr, red_ws, ep, st);
+    if (ep.mode == FEMOL_EPI_JACOBI) return launch_stencil<ND, 2>(p, mf, x, y, nullptr, nullptr, red_ws, ep, st);
+    return launch_stencil<ND, 0>(p, mf, x, y, dot_with, dot_out, red_ws, ep, st);
 }
 
 }  // namespace
 
 // K x for the solvers: the matrix-free stencil when the plan carries a descriptor for exactly this value array,
 // the CSR node-block kernel otherwise.
+static inline const femol_matrix_free* stencil_for(femol_plan_t p, const double* vals) {
+    const femol_matrix_free* mf = p->mf;
+    return (mf && mf->vals == vals && (p->ndof == 2 || p->ndof == 6)) ? mf : nullptr;
+}
+
 int femol_apply_launch(femol_plan_t p, const double* vals, const double* x, double* y, const double* dot_with,
                        double* dot_out, double* red_ws, cudaStream_t st) {
-    const femol_matrix_free* mf = p->mf;
-    if (mf && mf->vals == vals) {
-        if (p->ndof == 2) return launch_stencil<2>(p, mf, x, y, dot_with, dot_out, red_ws, st);
-        if (p->ndof == 6) return launch_stencil<6>(p, mf, x, y, dot_with, dot_out, red_ws, st);
+    const femol_epilogue none = {FEMOL_EPI_NONE, nullptr, nullptr, 0.0};
+    if (const femol_matrix_free* mf = stencil_for(p, vals)) {
+        if (p->ndof == 2) return launch_stencil_mode<2>(p, mf, x, y, dot_with, dot_out, red_ws, none, st);
+        return launch_stencil_mode<6>(p, mf, x, y, dot_with, dot_out, red_ws, none, st);
     }
     return femol_spmv_launch(p, vals, x, y, dot_with, dot_out, red_ws, st);
+}
+
+bool femol_apply_has_jacobi(femol_plan_t p, const double* vals) { return stencil_for(p, vals) != nullptr || p->ndof == 2; }
+
+int femol_apply_epilogue_launch(femol_plan_t p, const double* vals, const double* x, double* y, const femol_epilogue& ep,
+                                cudaStream_t st) {
+    if (ep.mode == FEMOL_EPI_NONE) return femol_apply_launch(p, vals, x, y, nullptr, nullptr, nullptr, st);
+    if (const femol_matrix_free* mf = stencil_for(p, vals)) {
+        if (p->ndof == 2) return launch_stencil_mode<2>(p, mf, x, y, nullptr, nullptr, nullptr, ep, st);
+        return launch_stencil_mode<6>(p, mf, x, y, nullptr, nullptr, nullptr, ep, st);
+    }
+    if (ep.mode == FEMOL_EPI_RESIDUAL) {
+        if (p->ndof == 2) return spmv_node_launch<2, 1>(p, vals, x, y, nullptr, nullptr, nullptr, st, ep.rhs);
+        if (p->ndof == 6) return spmv_node_launch<6, 1>(p, vals, x, y, nullptr, nullptr, nullptr, st, ep.rhs);
+    } else if (ep.mode == FEMOL_EPI_JACOBI && p->ndof == 2) {
+        return spmv_node_launch<2, 2>(p, vals, x, y, nullptr, nullptr, nullptr, st, ep.rhs, ep.dinv, ep.omega);
+    }
+    femol_set_error("femol_apply_epilogue_launch: mode %d not available for ndof %d", ep.mode, p->ndof);
+    return FEMOL_E_ARG;
 }
 
 extern "C" int femol_plan_set_matrix_free(femol_plan_t p, int64_t nx, int64_t ny, const double* e_base,

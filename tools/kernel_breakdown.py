@@ -26,6 +26,20 @@ def main():
         for _ in range(steps):
             opt.iterate()
         torch.cuda.synchronize()
+    # idle time between consecutive device activities (launch latency inside the graphs, host round trips)
+    ev = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events()
+                 if e.device_type.name != 'CPU'), key=lambda t: t[0])
+    if ev:
+        span = ev[-1][1] - ev[0][0]
+        gaps = [(max(0.0, b[0] - a[1]), b[2]) for a, b in zip(ev[:-1], ev[1:])]
+        small = [g for g, _ in gaps if g <= 5.0]
+        mid = [g for g, _ in gaps if 5.0 < g <= 50.0]
+        big = [(g, n) for g, n in gaps if g > 50.0]
+        print('span %.3f ms/step; idle %.3f ms/step: %d gaps <= 5 us (%.3f ms/step), %d gaps 5-50 us (%.3f ms/step), %d gaps > 50 us (%.3f ms/step)'
+              % (span / 1e3 / steps, sum(g for g, _ in gaps) / 1e3 / steps, len(small) // steps, sum(small) / 1e3 / steps,
+                 len(mid) // steps, sum(mid) / 1e3 / steps, len(big) // steps, sum(g for g, _ in big) / 1e3 / steps))
+        for g, n in sorted(big, reverse=True)[:12]:
+            print('   gap %8.1f us before %s' % (g, n[:90]))
     rows = []
     for e in prof.key_averages():
         t = getattr(e, 'device_time_total', None)
