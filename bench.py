@@ -272,25 +272,60 @@ def run_gpu(args):
         total_pcg = int(np.sum(pcg_iters))
         nu = problem.gmg_smoothing_steps
         gmg = problem.solver_info.get('preconditioner') == 'gmg'
-        # fine-level SpMV launches per PCG iteration: q = K p, plus (2 nu - 1) smoothing products + 1 residual
-        fine_spmv = total_pcg * ((1 + 2 * nu) if gmg else 1) + 2 * args.steps
-        roofline = {'kernel': 'spmv_node_kernel<2,4> on the fine level (q = K p and the V-cycle smoother / residual)',
+        matrix_free = bool(gmg and problem.matrix_free and problem.structured_grid_shape())
+        spmv_csr = {'kernel': 'spmv_node_kernel<2,4> (femol_spmv: assembled CSR values; unstructured meshes, coarse multigrid levels, block eigen-solver)',
                     'bound': 'hbm', 'achieved': spmv_survey / t_spmv / 1e9, 'peak': peak, 'unit': 'GB/s',
                     'frac': spmv_survey / t_spmv / 1e9 / peak, 'traffic': 828.0e6, 'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': spmv_survey, 'avg_launch_s': t_spmv,
                     'kernel_compulsory_bytes_per_launch': spmv_kernel,
                     'achieved_on_kernel_bytes': spmv_kernel / t_spmv / 1e9,
                     'frac_on_kernel_bytes': spmv_kernel / t_spmv / 1e9 / peak,
-                    'traffic_source': 'profiles/r01_ncu_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum)',
-                    'launches_in_timed_region': fine_spmv,
-                    'share_of_step': fine_spmv * t_spmv / dt if dt > 0 else None}
+                    'traffic_source': 'profiles/r01_ncu_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum)'}
+        if matrix_free:
+            # The fine-level products of the solve run matrix-free (csrc/stencil.cu): per PCG iteration one plain
+            # product (q = K p, fused dot), one with the residual epilogue and one with the Jacobi epilogue.
+            # Algorithmic bytes of one launch = what the operator needs from HBM: u read + y written (16 B / dof),
+            # one density per element, the Dirichlet mask; + rhs (modes 1, 2) and the block-diagonal inverse (mode 2).
+            nd = d.ndof
+            rv = torch.randn(n, dtype=torch.float64, device='cuda')
+            dinv = torch.empty(d.n_nodes * nd * nd, dtype=torch.float64, device='cuda')
+            F._lib.call('femol_precond_setup', d.plan, kv.data_ptr(), 2, dinv.data_ptr(), st)
+            base = 16 * n + 8 * n_elem + d.n_nodes
+            mf_bytes = [base, base + 8 * n, base + 8 * n + 8 * nd * n]
+            mf_t = [time_kernel(torch, lambda m=m: L.femol_apply_epilogue(d.plan, kv.data_ptr(), xv.data_ptr(), yv.data_ptr(), m,
+                                                                       rv.data_ptr(), dinv.data_ptr(), 0.7, st), 20)
+                    for m in range(3)]
+            per_it = [1, 1, 1] if nu == 1 else [1 + 2 * nu, 0, 0]
+            n_launch = [total_pcg * c for c in per_it]
+            n_launch[0] += 2 * args.steps                    # initial residual (+ restart check) of every solve
+            tot_b = sum(b * c for b, c in zip(mf_bytes, n_launch))
+            tot_t = sum(t * c for t, c in zip(mf_t, n_launch))
+            roofline = {'kernel': 'stencil_tile_kernel<2,false,32,16,4,mode 0|1|2>: matrix-free fine-level K p of PCG and of the V-cycle '
+                                  '(launch-weighted over the three epilogue modes)',
+                        'bound': 'hbm', 'achieved': tot_b / tot_t / 1e9, 'peak': peak, 'unit': 'GB/s',
+                        'frac': tot_b / tot_t / 1e9 / peak, 'traffic': 54.9e6, 'peak_source': peak_src,
+                        'traffic_source': 'profiles/r01_ncu_stencil_summary.md (mode 0 launch; the vectors are partly L2-resident between kernels)',
+                        'algorithmic_bytes_per_launch': tot_b / max(1, sum(n_launch)), 'avg_launch_s': tot_t / max(1, sum(n_launch)),
+                        'per_mode': [{'mode': m, 'bytes': mf_bytes[m], 'avg_launch_s': mf_t[m], 'GBps': mf_bytes[m] / mf_t[m] / 1e9,
+                                      'launches_in_timed_region': n_launch[m]} for m in range(3)],
+                        'equivalent_csr_bytes_per_launch': spmv_survey,
+                        'speedup_vs_csr_product': t_spmv / mf_t[0],
+                        'launches_in_timed_region': sum(n_launch),
+                        'share_of_step': tot_t / dt if dt > 0 else None,
+                        'note': 'issue-bound, not HBM-bound: 64 DFMA + staging per node, see DESIGN.md section 5'}
+        else:
+            fine_spmv = total_pcg * ((1 + 2 * nu) if gmg else 1) + 2 * args.steps
+            roofline = dict(spmv_csr)
+            roofline['launches_in_timed_region'] = fine_spmv
+            roofline['share_of_step'] = fine_spmv * t_spmv / dt if dt > 0 else None
         roofline_asm = {'kernel': 'femol_assemble = density_power + assemble_slots_kernel<2,4,9,4>', 'bound': 'hbm',
                         'achieved': asm_survey / t_asm / 1e9, 'peak': peak, 'unit': 'GB/s',
                         'frac': asm_survey / t_asm / 1e9 / peak, 'traffic': 938.0e6,
                         'algorithmic_bytes_per_launch': asm_survey, 'avg_launch_s': t_asm,
                         'kernel_compulsory_bytes_per_launch': asm_kernel,
                         'frac_on_kernel_bytes': asm_kernel / t_asm / 1e9 / peak,
-                        'launches_in_timed_region': args.steps}
+                        'launches_in_timed_region': args.steps,
+                        'share_of_step': args.steps * t_asm / dt if dt > 0 else None}
         cpu = None
         if not args.no_cpu_baseline:
             cdt, cval = cpu_sample(args.sample_nx, args.sample_ny, args.nx * args.ny, steps=1, warmup=0)
@@ -304,12 +339,13 @@ def run_gpu(args):
                 'config': {'workload': workload_name(args.nx, args.ny), 'ndof': n, 'nnz': nnz,
                            'pcg': {'precond': problem.solver_info.get('preconditioner', args.precond), 'rtol': args.rtol, 'iterations_per_step': pcg_iters,
                                    'warm_start': True},
-                           'l2_policy': 'inputs larger than L2 (CSR values %.0f MB per SpMV >> 126 MB L2)' % (8 * nnz / 1e6),
+                           'l2_policy': 'inputs larger than L2: one step touches %.0f MB of CSR values (assembly, level-1 operator) and %d MB of vectors per PCG iteration; 126 MB L2' % (8 * nnz / 1e6, 6 * 8 * n // 1000000),
                            'parallelism': 'one independent design per GPU' if world > 1 else 'single GPU',
                            'setup_s': setup_s},
                 'e2e': {'value': world * args.steps / dt_e2e, 'unit': UNIT, 'h2d_bytes_per_step': 8 * n_elem,
                         'd2h_bytes_per_step': 8 * n_elem + 64},
-                'gpu_launches': launches, 'roofline': roofline, 'roofline_assembly': roofline_asm,
+                'gpu_launches': launches, 'roofline': roofline, 'roofline_spmv_csr': spmv_csr,
+                'roofline_assembly': roofline_asm,
                 'cpu_baseline': cpu, 'clocks': clocks,
                 'trajectory': {'change': [l[0] for l in log], 'compliance': [l[1] for l in log],
                                'pcg_relres': [l[2] for l in log]}}

@@ -38,6 +38,7 @@ SIGNATURES = {
     'femol_spmv_csr': (c_int, [c_i64, P, P, P, P, P, P]),
     'femol_plan_set_matrix_free': (c_int, [P, c_i64, c_i64, P, P, P, P, P]),
     'femol_apply': (c_int, [P, P, P, P, P]),
+    'femol_apply_epilogue': (c_int, [P, P, P, P, c_int, P, P, c_dbl, P]),
     'femol_pcg_workspace_doubles': (c_i64, [P]),
     'femol_pcg': (c_int, [P, P, P, P, c_dbl, c_int, c_int, P, ctypes.POINTER(c_int), ctypes.POINTER(c_dbl), P]),
     'femol_gmg_create': (c_int, [c_i64, c_i64, c_int, P, P, c_int, c_dbl, P, ctypes.POINTER(c_vp)]),

@@ -48,8 +48,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // with one tile per CTA and ordinary loads ran at 1.4 TB/s - then consumes them in order.  Everything is
 // straight-line (no loop around the multiply), so the element-matrix operands are read from the constant bank
 // where they are used instead of being hoisted into, and spilled from, registers.
-template <int ND, bool COAT, int TI, int TJ, int NT, int MODE>
-__global__ void __launch_bounds__(TI * TJ, (ND == 2 || !COAT) ? 2 : 1)
+template <int ND, bool COAT, int TI, int TJ, int NT, int NPT, int MODE>
+__global__ void __launch_bounds__(TI * TJ / NPT, ND == 2 ? 3 : (COAT ? 1 : 2))
 stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int ny, int tiles_i, int n_tiles, int cta0,
                     const double* __restrict__ xpow, const uint8_t* __restrict__ fixed,
                     const double* __restrict__ u, double* __restrict__ y, const double* __restrict__ dot_with,
@@ -57,7 +57,8 @@ stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int
                     const double* __restrict__ dinv, double omega) {
     // 32-bit index arithmetic throughout (femol_plan_set_matrix_free checks n_dof < 2^31): the first version of
     // this kernel spent more than half of its issue slots on 64-bit address computation
-    constexpr int S = 4 * ND, PI = TI + 2, PJ = TJ + 2, WI = TI + 1, WJ = TJ + 1, H = ND / 2, NTH = TI * TJ;
+    constexpr int S = 4 * ND, PI = TI + 2, PJ = TJ + 2, WI = TI + 1, WJ = TJ + 1, H = ND / 2, NTH = TI * TJ / NPT;
+    static_assert(TJ % NPT == 0, "a thread owns NPT vertically adjacent nodes");
     constexpr int STAGE = PJ * PI * ND + WI * WJ + ((WI * WJ) & 1);   // doubles per tile buffer, 16-byte multiple
     constexpr int NPN = (PJ * PI + NTH - 1) / NTH;                    // patch nodes per thread (mask handling)
     extern __shared__ __align__(16) double s_mem[];
@@ -104,7 +105,9 @@ stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int
         }
     }
     double dot[1] = {0.0};
-    const int lj = threadIdx.x / TI, li = threadIdx.x - lj * TI;
+    // thread -> NPT vertically adjacent nodes (li, lj0 .. lj0 + NPT - 1): the element-matrix operand of every DFMA
+    // (one uniform constant-bank load) is then shared by NPT nodes, and neighbouring patches overlap in registers
+    const int lp = threadIdx.x / TI, li = threadIdx.x - lp * TI, lj0 = lp * NPT;
     int ti = ti0, tj = tj0;
 #pragma unroll
     for (int k = 0; k < NT; ++k) {
@@ -130,49 +133,65 @@ stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int
                 }
             __syncthreads();
         }
-        const int i = ti * TI + li, j = tj * TJ + lj;
+        const int i = ti * TI + li, jb = tj * TJ + lj0;
         if (++ti == tiles_i) { ti = 0; ++tj; }
-        if (i <= nx && j <= ny) {
-            const int n = j * npx + i;
-            double acc[ND];
+        if (i > nx || jb > ny) continue;
+        double acc[NPT][ND];
 #pragma unroll
-            for (int d = 0; d < ND; ++d) acc[d] = 0.0;
-            // the four elements around node (i, j): element (i - 1 + ex, j - 1 + ey) = tile element (li + ex, lj + ey)
+        for (int q = 0; q < NPT; ++q)
 #pragma unroll
-            for (int ey = 0; ey < 2; ++ey)
+            for (int d = 0; d < ND; ++d) acc[q][d] = 0.0;
+        // the four elements around a node, by relative position (ex, ey): element (i - 1 + ex, j - 1 + ey)
 #pragma unroll
-                for (int ex = 0; ex < 2; ++ex) {
-                    const double w = s_w[(li + ex) * WJ + lj + ey];
-                    // local index of node (i, j) in that element: Q4 order (0,0) (1,0) (1,1) (0,1)
-                    const int lx = 1 - ex, ly = 1 - ey;
-                    const int a = ly == 0 ? lx : 3 - lx;
-                    double part[ND], partc[ND];
+        for (int ey = 0; ey < 2; ++ey)
 #pragma unroll
-                    for (int d = 0; d < ND; ++d) { part[d] = 0.0; partc[d] = 0.0; }
+            for (int ex = 0; ex < 2; ++ex) {
+                // local index of the node in that element: Q4 order (0,0) (1,0) (1,1) (0,1)
+                const int lx = 1 - ex, ly = 1 - ey;
+                const int a = ly == 0 ? lx : 3 - lx;
+                double part[NPT][ND], partc[NPT][ND];
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int bx = (b == 1 || b == 2) ? 1 : 0, by = (b >= 2) ? 1 : 0;
-                        double ub[ND];                              // node (ei + bx, ej + by) of the staged patch
+                for (int q = 0; q < NPT; ++q)
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) { part[q][d] = 0.0; partc[q][d] = 0.0; }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int bx = (b == 1 || b == 2) ? 1 : 0, by = (b >= 2) ? 1 : 0;
+                    double ub[NPT][ND];                         // node (ei + bx, ej + by) of the staged patch, per owned node
+#pragma unroll
+                    for (int q = 0; q < NPT; ++q)
 #pragma unroll
                         for (int d = 0; d < ND; d += 2) {
-                            const double2 v = *reinterpret_cast<const double2*>(s_u + ((lj + ey + by) * PI + li + ex + bx) * ND + d);
-                            ub[d] = v.x; ub[d + 1] = v.y;
+                            const double2 v = *reinterpret_cast<const double2*>(s_u + ((lj0 + q + ey + by) * PI + li + ex + bx) * ND + d);
+                            ub[q][d] = v.x; ub[q][d + 1] = v.y;
                         }
 #pragma unroll
-                        for (int da = 0; da < ND; ++da) {
-                            const int row = (a * ND + da) * S + b * ND;
+                    for (int da = 0; da < ND; ++da) {
+                        const int row = (a * ND + da) * S + b * ND;
 #pragma unroll
-                            for (int db = 0; db < ND; ++db) {
-                                part[da] = fma(km.base[row + db], ub[db], part[da]);
-                                if (COAT) partc[da] = fma(km.coat[row + db], ub[db], partc[da]);
+                        for (int db = 0; db < ND; ++db) {
+#pragma unroll
+                            for (int q = 0; q < NPT; ++q) {
+                                part[q][da] = fma(km.base[row + db], ub[q][db], part[q][da]);
+                                if (COAT) partc[q][da] = fma(km.coat[row + db], ub[q][db], partc[q][da]);
                             }
                         }
                     }
-                    // outside the mesh w is 0 (zero fill); the coating's base part is unweighted, so test explicitly
-                    const bool inside = (unsigned)(i - 1 + ex) < (unsigned)nx && (unsigned)(j - 1 + ey) < (unsigned)ny;
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) acc[d] += COAT ? (inside ? fma(w, partc[d], part[d]) : 0.0) : w * part[d];
                 }
+#pragma unroll
+                for (int q = 0; q < NPT; ++q) {
+                    const double w = s_w[(li + ex) * WJ + lj0 + q + ey];
+                    // outside the mesh w is 0 (zero fill); the coating's base part is unweighted, so test explicitly
+                    const bool inside = (unsigned)(i - 1 + ex) < (unsigned)nx && (unsigned)(jb + q - 1 + ey) < (unsigned)ny;
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) acc[q][d] += COAT ? (inside ? fma(w, partc[q][d], part[q][d]) : 0.0) : w * part[q][d];
+                }
+            }
+#pragma unroll
+        for (int q = 0; q < NPT; ++q) {
+            const int j = jb + q;
+            if (j > ny) break;
+            const int n = j * npx + i;
             // rows of fixed dofs are the identity
             const uint32_t frow = fixed ? __ldg(&fixed[n]) : 0u;
             const double* un = u + (size_t)n * ND;
@@ -180,20 +199,20 @@ stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int
             if (frow) {
 #pragma unroll
                 for (int d = 0; d < ND; ++d)
-                    if ((frow >> d) & 1u) acc[d] = __ldg(un + d);
+                    if ((frow >> d) & 1u) acc[q][d] = __ldg(un + d);
             }
             if (MODE == 1) {            // y = rhs - K u
 #pragma unroll
                 for (int d = 0; d < ND; d += 2) {
-                    const double2 q = __ldg(reinterpret_cast<const double2*>(rhs + (size_t)n * ND + d));
-                    acc[d] = q.x - acc[d]; acc[d + 1] = q.y - acc[d + 1];
+                    const double2 r2 = __ldg(reinterpret_cast<const double2*>(rhs + (size_t)n * ND + d));
+                    acc[q][d] = r2.x - acc[q][d]; acc[q][d + 1] = r2.y - acc[q][d + 1];
                 }
             } else if (MODE == 2) {     // y = u + omega Dinv (rhs - K u)
                 double res[ND];
 #pragma unroll
                 for (int d = 0; d < ND; d += 2) {
-                    const double2 q = __ldg(reinterpret_cast<const double2*>(rhs + (size_t)n * ND + d));
-                    res[d] = q.x - acc[d]; res[d + 1] = q.y - acc[d + 1];
+                    const double2 r2 = __ldg(reinterpret_cast<const double2*>(rhs + (size_t)n * ND + d));
+                    res[d] = r2.x - acc[q][d]; res[d + 1] = r2.y - acc[q][d + 1];
                 }
                 const double* B = dinv + (size_t)n * ND * ND;
 #pragma unroll
@@ -204,16 +223,16 @@ stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int
                         const double2 b2 = __ldg(reinterpret_cast<const double2*>(B + da * ND + db));
                         t = fma(b2.x, res[db], t); t = fma(b2.y, res[db + 1], t);
                     }
-                    acc[da] = __ldg(un + da) + omega * t;
+                    acc[q][da] = __ldg(un + da) + omega * t;
                 }
             }
 #pragma unroll
             for (int d = 0; d < ND; d += 2) {
-                const double2 o = make_double2(acc[d], acc[d + 1]);
+                const double2 o = make_double2(acc[q][d], acc[q][d + 1]);
                 *reinterpret_cast<double2*>(yn + d) = o;
                 if (MODE == 0 && dot_with) {
-                    const double2 q = __ldg(reinterpret_cast<const double2*>(dot_with + (size_t)n * ND + d));
-                    dot[0] += o.x * q.x + o.y * q.y;
+                    const double2 w2 = __ldg(reinterpret_cast<const double2*>(dot_with + (size_t)n * ND + d));
+                    dot[0] += o.x * w2.x + o.y * w2.y;
                 }
             }
         }
@@ -225,11 +244,11 @@ stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int
 template <int ND, bool COAT, int MODE>
 int launch_stencil_c(femol_plan_t p, const femol_matrix_free* mf, const double* x, double* y, const double* dot_with,
                      double* dot_out, double* red_ws, const femol_epilogue& ep, cudaStream_t st) {
-    constexpr int TI = 32, TJ = ND == 2 ? 16 : 8, NT = 4;
+    constexpr int TI = 32, TJ = ND == 2 ? 16 : 8, NT = 4, NPT = ND == 2 ? 2 : 1;
     constexpr int WW = (TI + 1) * (TJ + 1);
     constexpr size_t smem = (size_t)NT * ((TJ + 2) * (TI + 2) * ND + WW + (WW & 1)) * sizeof(double);
     static bool configured = false;
-    auto kern = stencil_tile_kernel<ND, COAT, TI, TJ, NT, MODE>;
+    auto kern = stencil_tile_kernel<ND, COAT, TI, TJ, NT, NPT, MODE>;
     if (!configured) {
         FEMOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
@@ -246,7 +265,7 @@ int launch_stencil_c(femol_plan_t p, const femol_matrix_free* mf, const double* 
     const bool fused = n_cta <= max_grid;
     for (int64_t c0 = 0; c0 < n_cta; c0 += max_grid) {
         const int64_t nb = n_cta - c0 < max_grid ? n_cta - c0 : max_grid;
-        kern<<<(int)nb, TI * TJ, smem, st>>>(km, (int)mf->nx, (int)mf->ny, tiles_i, (int)n_tiles, (int)c0, mf->xpow, mf->fixed, x, y,
+        kern<<<(int)nb, TI * TJ / NPT, smem, st>>>(km, (int)mf->nx, (int)mf->ny, tiles_i, (int)n_tiles, (int)c0, mf->xpow, mf->fixed, x, y,
                                              fused ? dot_with : nullptr, fused ? dot_out : nullptr, red_ws, ep.rhs, ep.dinv,
                                              ep.omega);
         FEMOL_LAUNCH_CHECK();
@@ -327,6 +346,17 @@ extern "C" int femol_plan_set_matrix_free(femol_plan_t p, int64_t nx, int64_t ny
     p->mf->has_coat = e_coat != nullptr;
     if (e_coat) memcpy(p->mf->e_coat, e_coat, s2 * sizeof(double));
     return FEMOL_OK;
+}
+
+// y = op(K x) with the multigrid epilogues (mode 0: K x; 1: rhs - K x; 2: x + omega Dinv (rhs - K x)) through the
+// operator the solvers use; exposed for the parity tests and the per-kernel timings of bench.py
+extern "C" int femol_apply_epilogue(femol_plan_t p, const double* vals, const double* x, double* y, int mode,
+                                    const double* rhs, const double* dinv, double omega, void* stream) {
+    FEMOL_REQUIRE(p && vals && x && y && x != y, "femol_apply_epilogue: null or aliased argument");
+    FEMOL_REQUIRE(mode >= 0 && mode <= 2 && (mode == 0 || rhs) && (mode != 2 || dinv), "femol_apply_epilogue: bad mode / missing operand");
+    FEMOL_REQUIRE(mode != 2 || femol_apply_has_jacobi(p, vals), "femol_apply_epilogue: mode 2 needs ndof = 2 or the matrix-free operator");
+    const femol_epilogue ep = {mode, rhs, dinv, omega};
+    return femol_apply_epilogue_launch(p, vals, x, y, ep, (cudaStream_t)stream);
 }
 
 // y = K x through whichever operator the solvers would use (tests compare it with the CSR product)

@@ -116,6 +116,12 @@ int femol_spmv_csr(int64_t n_rows, const int32_t* indptr, const int32_t* indices
 int femol_plan_set_matrix_free(femol_plan_t plan, int64_t nx, int64_t ny, const double* e_base_host,
                                const double* e_coat_host, const double* xpow, const uint8_t* fixed, const double* vals);
 int femol_apply(femol_plan_t plan, const double* vals, const double* x, double* y, void* stream);
+/* The same product with the multigrid epilogues fused in (y must not alias x):
+ *   mode 0  y = K x          mode 1  y = rhs - K x          mode 2  y = x + omega * Dinv (rhs - K x)
+ * Dinv = femol_precond_setup(..., FEMOL_PRECOND_BLOCK_JACOBI) ([n_nodes][ndof][ndof]).  Mode 2 is available for
+ * ndof = 2 and, with the matrix-free operator, for ndof = 6. */
+int femol_apply_epilogue(femol_plan_t plan, const double* vals, const double* x, double* y, int mode,
+                         const double* rhs, const double* dinv, double omega, void* stream);
 
 /* ---- K5: preconditioned conjugate gradients (replaces spsolve, FEM.py:258-265) --------------
  * Solves A u = f from the initial guess in u.  ws: femol_pcg_workspace_doubles(plan) doubles.

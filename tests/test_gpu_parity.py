@@ -706,3 +706,35 @@ def test_matrix_free_and_assembled_solves_agree(F):
             assert p.solver_info['converged']
     for pc in ('gmg', 'block_jacobi'):
         assert rel(out[True, pc], out[False, pc]) < 1e-8
+
+
+@pytest.mark.parametrize('nx,ny,model,matrix_free', [(40, 21, 'plane', True), (40, 21, 'plane', False), (19, 9, 'plate', True),
+                                                     (1, 1, 'plane', True), (130, 70, 'plane', True)])
+def test_product_epilogues(F, nx, ny, model, matrix_free):
+    """The fused multigrid epilogues of the product (residual and damped block-Jacobi sweep) against numpy."""
+    import torch
+    p, x = _gmg_problem(F, nx, ny, model)
+    p.matrix_free = matrix_free
+    p.assemble('K', X={'quad': x}, p=3)
+    d = p.device
+    nd = p.N_dof
+    rng = np.random.default_rng(5)
+    xs, rhs = rng.standard_normal(d.n), rng.standard_normal(d.n)
+    xd, rd = torch.from_numpy(xs).cuda(), torch.from_numpy(rhs).cuda()
+    dinv = torch.empty(d.n_nodes * nd * nd, dtype=torch.float64, device='cuda')
+    F._lib.call('femol_precond_setup', d.plan, p.K_values.data_ptr(), 2, dinv.data_ptr(), F._lib.stream())
+    K = p.K
+    Kx = K @ xs
+    y = torch.empty_like(xd)
+    F._lib.call('femol_apply_epilogue', d.plan, p.K_values.data_ptr(), xd.data_ptr(), y.data_ptr(), 1, rd.data_ptr(), None, 0.0, F._lib.stream())
+    assert rel(y.cpu().numpy(), rhs - Kx) < 1e-13
+    D = dinv.cpu().numpy().reshape(d.n_nodes, nd, nd)
+    Kd = K.toarray()
+    for i in (0, d.n_nodes // 2, d.n_nodes - 1):    # Dinv really is the inverse of the node's diagonal block
+        blk = Kd[i * nd:(i + 1) * nd, i * nd:(i + 1) * nd]
+        assert np.allclose(D[i] @ blk, np.eye(nd), atol=1e-10)
+    ref = xs + 0.7 * np.einsum('nab,nb->na', D, (rhs - Kx).reshape(-1, nd)).reshape(-1)
+    F._lib.call('femol_apply_epilogue', d.plan, p.K_values.data_ptr(), xd.data_ptr(), y.data_ptr(), 2, rd.data_ptr(), dinv.data_ptr(), 0.7, F._lib.stream())
+    assert rel(y.cpu().numpy(), ref) < 1e-13
+    with pytest.raises(F._lib.FemolError):
+        F._lib.call('femol_apply_epilogue', d.plan, p.K_values.data_ptr(), xd.data_ptr(), xd.data_ptr(), 0, None, None, 0.0, F._lib.stream())
