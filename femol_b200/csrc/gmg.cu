@@ -17,10 +17,13 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "spmv.cuh"
 
 extern "C" int femol_precond_setup(femol_plan_t p, const double* vals, int kind, double* dinv, void* stream);
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -48,6 +51,10 @@ struct femol_gmg {
     int64_t nc;
     void* d_desc;        // device array of LevelDesc (all levels) for the fused coarse V-cycle
     int fused_from;      // first level handled by the single-CTA kernel (n_levels = none)
+    int cluster_from;    // nu = 1: first level handled by the cluster kernel (n_levels = none), ...
+    int solo_from;       // ... first level CTA 0 handles alone, ...
+    int cluster_size;    // ... CTAs per cluster (0: unavailable)
+    int hint_iters;      // CG iterations of the previous solve with this hierarchy (sizes the first batch)
 };
 
 namespace {
@@ -554,12 +561,258 @@ coarse_vcycle_kernel(const LevelDesc* __restrict__ lv, int l0, int last, int nu,
     }
 }
 
+// ---- cluster coarse V-cycle (nu = 1): the launch-bound levels in ONE kernel on a thread-block cluster -------------
+// Levels whose operator is at most a few MB (cfg 2: 250 x 125 and below) cost ~6 us per kernel in launch latency and
+// gaps, five kernels per level and iteration, plus 87 us for the single-CTA kernel above: a quarter of a CG
+// iteration.  Here a cluster of up to 16 CTAs (16 SMs, hardware cluster barrier between the phases) walks levels
+// [l0, solo) together; the smallest levels [solo, last], where even a cluster barrier costs more than the work, are
+// done by CTA 0 alone with __syncthreads() while the others wait at one cluster barrier.  Per level: product with
+// residual epilogue, restriction + first sweep of the next level, prolongation (out of place), product with Jacobi
+// epilogue - four barriers.  A warp owns 32 / ND whole nodes, so the block-Jacobi epilogue is a few shuffles.
+struct Team {
+    int tid, stride;
+    bool solo;
+};
+
+__device__ __forceinline__ void team_sync(const Team& tm) {
+    if (tm.solo) __syncthreads();
+    else cg::this_cluster().sync();
+}
+
+// MODE 1: y = rhs - K x ;  MODE 2: y = x + omega Dinv (rhs - K x)      (x, rhs, y: vectors written inside this kernel)
+template <int ND, int MODE>
+__device__ void team_product(const LevelDesc& L, const double* x, const double* rhs, double* y, double omega, const Team& tm) {
+    constexpr int NPW = 32 / ND;
+    const int lane = threadIdx.x & 31;
+    const int nl = lane / ND, da = lane - nl * ND;
+    const int64_t warp = tm.tid >> 5, n_warps = tm.stride >> 5;
+    for (int64_t node0 = warp * NPW; node0 < L.n_nodes; node0 += n_warps * NPW) {
+        const int64_t i = node0 + nl;
+        const bool valid = nl < NPW && i < L.n_nodes;
+        double res = 0.0;
+        if (valid) {
+            const int pb = __ldg(&L.adj_ptr[i]), len = __ldg(&L.adj_ptr[i + 1]) - pb;
+            const double* a = L.vals + (int64_t)ND * ND * pb + (int64_t)da * len * ND;
+            double acc = 0.0;
+            for (int k = 0; k < len; ++k) {
+                const double* xv = x + (int64_t)__ldg(&L.adj_idx[pb + k]) * ND;
+#pragma unroll
+                for (int d = 0; d < ND; d += 2) {
+                    const double2 x2 = __ldcg(reinterpret_cast<const double2*>(xv + d));
+                    acc = fma(__ldg(&a[k * ND + d]), x2.x, acc);
+                    acc = fma(__ldg(&a[k * ND + d + 1]), x2.y, acc);
+                }
+            }
+            res = __ldcg(&rhs[i * ND + da]) - acc;
+        }
+        if (MODE == 1) {
+            if (valid) y[i * ND + da] = res;
+        } else {
+            double t = 0.0;
+#pragma unroll
+            for (int b = 0; b < ND; ++b) {
+                const double rb = __shfl_sync(0xffffffffu, res, nl * ND + b);
+                if (valid) t = fma(__ldg(&L.dinv[(i * ND + da) * ND + b]), rb, t);
+            }
+            if (valid) y[i * ND + da] = __ldcg(&x[i * ND + da]) + omega * t;
+        }
+    }
+}
+
+// e = omega Dinv r
+template <int ND>
+__device__ void team_jacobi_first(const LevelDesc& L, double omega, const double* r, double* e, const Team& tm) {
+    for (int64_t i = tm.tid; i < L.n_nodes; i += tm.stride) {
+        double d[ND];
+#pragma unroll
+        for (int a = 0; a < ND; ++a) d[a] = __ldcg(&r[i * ND + a]);
+        const double* B = L.dinv + i * ND * ND;
+#pragma unroll
+        for (int a = 0; a < ND; ++a) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int b = 0; b < ND; ++b) sacc += __ldg(&B[a * ND + b]) * d[b];
+            e[i * ND + a] = omega * sacc;
+        }
+    }
+}
+
+// r_c = P^T r_f  and, if `smooth_c`, the coarse level's first sweep e_c = omega Dinv_c r_c
+template <int ND>
+__device__ void team_restrict(const LevelDesc& F, const LevelDesc& C, const double* rf, double* rc, bool smooth_c,
+                              double omega, double* ec, const Team& tm) {
+    for (int64_t t = tm.tid; t < C.n_nodes; t += tm.stride) {
+        const int64_t J = t / (C.nx + 1), I = t - J * (C.nx + 1);
+        const int64_t ic = min(2 * I, F.nx), jc = min(2 * J, F.ny);
+        double acc[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) acc[d] = 0.0;
+        for (int dj = -1; dj <= 1; ++dj) {
+            const int64_t j = jc + dj;
+            if (j < 0 || j > F.ny) continue;
+            int64_t J0, J1; double v0, v1;
+            cmap1d(j, F.ny, J0, v0, J1, v1);
+            const double wy = (J0 == J ? v0 : 0.0) + (J1 == J && v1 != 0.0 ? v1 : 0.0);
+            if (wy == 0.0) continue;
+            for (int di = -1; di <= 1; ++di) {
+                const int64_t i = ic + di;
+                if (i < 0 || i > F.nx) continue;
+                int64_t I0, I1; double u0, u1;
+                cmap1d(i, F.nx, I0, u0, I1, u1);
+                const double wx = (I0 == I ? u0 : 0.0) + (I1 == I && u1 != 0.0 ? u1 : 0.0);
+                if (wx == 0.0) continue;
+                const int64_t nf = j * (F.nx + 1) + i;
+                const uint32_t fm = F.fixed ? F.fixed[nf] : 0u;
+                const double w = wx * wy;
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                    if (!((fm >> d) & 1u)) acc[d] += w * __ldcg(&rf[nf * ND + d]);
+            }
+        }
+        const uint32_t cm = C.fixed ? C.fixed[t] : 0u;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            if ((cm >> d) & 1u) acc[d] = 0.0;
+            rc[t * ND + d] = acc[d];
+        }
+        if (smooth_c) {
+            const double* B = C.dinv + t * ND * ND;
+#pragma unroll
+            for (int a = 0; a < ND; ++a) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int b = 0; b < ND; ++b) sacc += __ldg(&B[a * ND + b]) * acc[b];
+                ec[t * ND + a] = omega * sacc;
+            }
+        }
+    }
+}
+
+// out = e_f + P e_c
+template <int ND>
+__device__ void team_prolong(const LevelDesc& F, const LevelDesc& C, const double* ec, const double* ef, double* out, const Team& tm) {
+    for (int64_t t = tm.tid; t < F.n_nodes; t += tm.stride) {
+        const int64_t j = t / (F.nx + 1), i = t - j * (F.nx + 1);
+        int64_t I0, I1, J0, J1; double u0, u1, v0, v1;
+        cmap1d(i, F.nx, I0, u0, I1, u1);
+        cmap1d(j, F.ny, J0, v0, J1, v1);
+        const uint32_t fm = F.fixed ? F.fixed[t] : 0u;
+        const int64_t c00 = J0 * (C.nx + 1) + I0, c10 = J0 * (C.nx + 1) + I1, c01 = J1 * (C.nx + 1) + I0, c11 = J1 * (C.nx + 1) + I1;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            double v = 0.0;
+            if (!((fm >> d) & 1u)) {
+                v = u0 * v0 * __ldcg(&ec[c00 * ND + d]);
+                if (u1 != 0.0) v += u1 * v0 * __ldcg(&ec[c10 * ND + d]);
+                if (v1 != 0.0) { v += u0 * v1 * __ldcg(&ec[c01 * ND + d]); if (u1 != 0.0) v += u1 * v1 * __ldcg(&ec[c11 * ND + d]); }
+            }
+            out[t * ND + d] = __ldcg(&ef[t * ND + d]) + v;
+        }
+    }
+}
+
+template <int ND>
+__device__ void team_down(const LevelDesc* lv, int l, int l0, int last, double omega, const double* r0, double* e0, const Team& tm) {
+    const LevelDesc L = lv[l], C = lv[l + 1];
+    const double* r = l == l0 ? r0 : L.r;
+    double* e = l == l0 ? e0 : L.e;
+    team_product<ND, 1>(L, e, r, L.t, 0.0, tm);                       // t = r - K e
+    team_sync(tm);
+    team_restrict<ND>(L, C, L.t, C.r, l + 1 != last, omega, C.e, tm);  // r_c (and e_c = omega Dinv r_c)
+    team_sync(tm);
+}
+
+template <int ND>
+__device__ void team_up(const LevelDesc* lv, int l, int l0, double omega, const double* r0, double* e0, const Team& tm) {
+    const LevelDesc L = lv[l], C = lv[l + 1];
+    const double* r = l == l0 ? r0 : L.r;
+    double* e = l == l0 ? e0 : L.e;
+    team_prolong<ND>(L, C, C.e, e, L.t, tm);                           // t = e + P e_c
+    team_sync(tm);
+    team_product<ND, 2>(L, L.t, r, e, omega, tm);                      // e = t + omega Dinv (r - K t)
+    team_sync(tm);
+}
+
+// levels l0 .. last with l0 < last; e0 must already hold the first sweep omega Dinv r0 (the caller's restriction wrote
+// it); [l0, solo) on the whole cluster, [solo, last] on CTA 0, l0 <= solo <= last
+template <int ND>
+__global__ void __launch_bounds__(1024)
+cluster_vcycle_kernel(const LevelDesc* __restrict__ lv, int l0, int solo, int last, double omega,
+                      const double* __restrict__ coarse_inv, const double* r0, double* e0) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), csz = (int)cluster.num_blocks();
+    const Team all = {rank * (int)blockDim.x + (int)threadIdx.x, csz * (int)blockDim.x, false};
+    const Team one = {(int)threadIdx.x, (int)blockDim.x, true};
+    for (int l = l0; l < solo; ++l) team_down<ND>(lv, l, l0, last, omega, r0, e0, all);
+    if (rank == 0) {
+        for (int l = solo; l < last; ++l) team_down<ND>(lv, l, l0, last, omega, r0, e0, one);
+        {   // coarsest: dense inverse
+            const LevelDesc L = lv[last];
+            const int n = (int)(L.n_nodes * ND);
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+            for (int i = warp; i < n; i += nw) {
+                double sacc = 0.0;
+                for (int j = lane; j < n; j += 32) sacc += __ldg(&coarse_inv[(int64_t)i * n + j]) * __ldcg(&L.r[j]);
+                sacc = warp_sum(sacc);
+                if (lane == 0) L.e[i] = sacc;
+            }
+            __syncthreads();
+        }
+        for (int l = last - 1; l >= solo; --l) team_up<ND>(lv, l, l0, omega, r0, e0, one);
+    }
+    if (solo > l0) cluster.sync();      // the solo levels' correction is visible to the whole cluster
+    for (int l = solo - 1; l >= l0; --l) team_up<ND>(lv, l, l0, omega, r0, e0, all);
+}
+
 int grid_for(int64_t n, int block = 256) {
     int64_t g = (n + block - 1) / block;
     const int64_t cap = (int64_t)femol_sm_count() * 8;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
+}
+
+// largest cluster (16, 8, 4, 2, 1 CTAs of 1024 threads) the device can co-schedule for the cluster kernel
+template <int ND>
+int cluster_size_probe() {
+    auto kern = cluster_vcycle_kernel<ND>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
+    const char* env = getenv("FEMOL_GMG_CLUSTER_SIZE");
+    int want = env ? atoi(env) : 16;
+    for (int cs = want; cs >= 1; cs >>= 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs); cfg.blockDim = dim3(1024);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n >= 1) return cs;
+        cudaGetLastError();
+    }
+    return 0;
+}
+int cluster_size_for(int nd) {
+    static int cached[2] = {-1, -1};
+    int& c = cached[nd == 2 ? 0 : 1];
+    if (c < 0) c = nd == 2 ? cluster_size_probe<2>() : cluster_size_probe<6>();
+    return c;
+}
+
+template <int ND>
+int launch_cluster_vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st) {
+    const int solo = g->solo_from < l ? l : g->solo_from;
+    const int cs = solo > l ? g->cluster_size : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    FEMOL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, cluster_vcycle_kernel<ND>, (const LevelDesc*)g->d_desc, l, solo, g->n_levels - 1,
+                                        g->omega, (const double*)g->coarse_inv, r, e));
+    femol_count_launch();
+    return FEMOL_OK;
 }
 
 template <int ND>
@@ -582,9 +835,11 @@ int smooth(femol_gmg* g, int l, const double* r, double* e, bool zero_start, cud
 
 // `presmoothed`: e already holds the first sweep omega Dinv r (written by the restriction that produced r)
 template <int ND>
-int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, bool presmoothed = false) {
+int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, bool presmoothed = false,
+           double* rz_out = nullptr, double* red_ws = nullptr, bool* rz_fused = nullptr) {
     Level& L = g->lv[l];
-    if (l >= 1 && l >= g->fused_from && g->d_desc) {
+    if (g->nu == 1 && l >= 1 && l >= g->cluster_from && presmoothed) return launch_cluster_vcycle<ND>(g, l, r, e, st);
+    if (g->nu != 1 && l >= 1 && l >= g->fused_from && g->d_desc) {
         coarse_vcycle_kernel<ND><<<1, 1024, 0, st>>>((const LevelDesc*)g->d_desc, l, g->n_levels - 1, g->nu, g->omega, g->coarse_inv, r, e);
         FEMOL_LAUNCH_CHECK();
         return FEMOL_OK;
@@ -608,10 +863,10 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, boo
             jacobi_kernel<ND, true><<<grid_for(L.n_nodes), 256, 0, st>>>(L.n_nodes, g->omega, L.dinv, r, nullptr, e);
             FEMOL_LAUNCH_CHECK();
         }
-        const femol_epilogue res = {FEMOL_EPI_RESIDUAL, r, nullptr, 0.0};
+        const femol_epilogue res = {FEMOL_EPI_RESIDUAL, r, nullptr, 0.0, nullptr, nullptr};
         rc = femol_apply_epilogue_launch(L.plan, L.vals, e, L.t, res, st);
         if (rc != FEMOL_OK) return rc;
-        const bool coarse_regular = !(l + 1 >= g->fused_from && g->d_desc) && (l + 1 != g->n_levels - 1);
+        const bool coarse_regular = l + 1 != g->n_levels - 1;   // every smoothing level starts from omega Dinv r
         restrict_kernel<ND><<<grid_for(C.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, C.ny, L.fixed, C.fixed, L.t, C.r,
                                                                  coarse_regular ? C.dinv : nullptr, g->omega, C.e);
         FEMOL_LAUNCH_CHECK();
@@ -620,7 +875,9 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, boo
         if (femol_apply_has_jacobi(L.plan, L.vals)) {
             prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e, L.t);
             FEMOL_LAUNCH_CHECK();
-            const femol_epilogue jac = {FEMOL_EPI_JACOBI, r, L.dinv, g->omega};
+            // level 0 inside CG: the last kernel of the V-cycle also delivers r . z
+            const femol_epilogue jac = {FEMOL_EPI_JACOBI, r, L.dinv, g->omega, rz_out, red_ws};
+            if (rz_out && rz_fused) *rz_fused = true;
             return femol_apply_epilogue_launch(L.plan, L.vals, L.t, e, jac, st);
         }
         prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e, e);
@@ -644,8 +901,19 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, boo
 
 }  // namespace
 
-int femol_gmg_vcycle_internal(femol_gmg* g, const double* r, double* z, cudaStream_t st) {
-    return g->nd == 2 ? vcycle<2>(g, 0, r, z, st) : vcycle<6>(g, 0, r, z, st);
+// remembers the CG iteration count of the last solve (set >= 0 stores, set < 0 only reads)
+int femol_gmg_iteration_hint(femol_gmg* g, int set) {
+    if (set >= 0) g->hint_iters = set;
+    return g->hint_iters;
+}
+
+// z = V(r).  With rz_out (device scalar) the product r . z is requested as well; *rz_fused tells whether the V-cycle's
+// last kernel delivered it (otherwise the caller computes it).
+int femol_gmg_vcycle_internal(femol_gmg* g, const double* r, double* z, cudaStream_t st, double* rz_out, double* red_ws,
+                              bool* rz_fused) {
+    if (rz_fused) *rz_fused = false;
+    return g->nd == 2 ? vcycle<2>(g, 0, r, z, st, false, rz_out, red_ws, rz_fused)
+                      : vcycle<6>(g, 0, r, z, st, false, rz_out, red_ws, rz_fused);
 }
 
 extern "C" int femol_gmg_destroy(femol_gmg* g) {
@@ -741,6 +1009,30 @@ extern "C" int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t f
         }
         GCHECK(cudaMalloc(&g->d_desc, sizeof(h)));
         GCHECK(cudaMemcpyAsync(g->d_desc, h, sizeof(h), cudaMemcpyHostToDevice, st));
+        // cluster kernel (nu = 1): levels whose operator is at most FEMOL_GMG_CLUSTER_MB, the smallest ones solo
+        const int last = g->n_levels - 1;
+        g->cluster_from = g->solo_from = g->n_levels;
+        g->cluster_size = 0;
+        g->hint_iters = 0;
+        const char* env_mb = getenv("FEMOL_GMG_CLUSTER_MB");
+        const double cluster_mb = env_mb ? atof(env_mb) : 0.7;   // measured on cfg 2 (it/s): 12 MB 46.6, 3 MB 49.0, 0.7 MB 49.4, off 49.5
+        const char* env_solo = getenv("FEMOL_GMG_SOLO_NODES");
+        const long long solo_nodes = env_solo ? atoll(env_solo) : 700;
+        if (g->nu == 1 && cluster_mb > 0) {
+            for (int k = 1; k < last; ++k) {
+                const double mb = (double)g->lv[k].plan->nnz_node * g->nd * g->nd * 8.0 / 1e6;
+                if (mb <= cluster_mb) { g->cluster_from = k; break; }
+            }
+            if (g->cluster_from < last) {
+                g->solo_from = last;
+                for (int k = g->cluster_from; k < last; ++k)
+                    if (g->lv[k].n_nodes <= solo_nodes) { g->solo_from = k; break; }
+                g->cluster_size = cluster_size_for(g->nd);
+                if (g->cluster_size == 0) g->cluster_from = g->solo_from = g->n_levels;
+            } else {
+                g->cluster_from = g->n_levels;
+            }
+        }
     }
     GCHECK(cudaStreamSynchronize(st));
 #undef GCHECK
@@ -799,5 +1091,5 @@ extern "C" int femol_gmg_info(femol_gmg* g, int64_t* h_info /* [0]=levels, then 
 // z = V-cycle(r): one application of the preconditioner (exposed for tests and for LOBPCG)
 extern "C" int femol_gmg_apply(femol_gmg* g, const double* r, double* z, void* stream) {
     FEMOL_REQUIRE(g && r && z, "femol_gmg_apply: null argument");
-    return femol_gmg_vcycle_internal(g, r, z, (cudaStream_t)stream);
+    return femol_gmg_vcycle_internal(g, r, z, (cudaStream_t)stream, nullptr, nullptr, nullptr);
 }

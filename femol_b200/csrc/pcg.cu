@@ -15,7 +15,7 @@
 namespace {
 
 // device scalar slots
-enum { S_RZ0 = 0, S_RZ1 = 1, S_PQ = 2, S_RR = 3, S_FF = 4, S_DONE = 5, S_ITER = 6, S_TOL2 = 7, S_NSLOT = 16 };
+enum { S_RZ0 = 0, S_RZ1 = 1, S_PQ = 2, S_RR = 3, S_FF = 4, S_DONE = 5, S_ITER = 6, S_TOL2 = 7, S_RZN = 8, S_RZO = 9, S_NSLOT = 16 };
 
 constexpr int VEC_THREADS = 256;
 
@@ -298,13 +298,14 @@ extern "C" int femol_pcg(femol_plan_t p, const double* vals, const double* f, do
 // =====================================================================================================
 #include <stdlib.h>
 struct femol_gmg;
-int femol_gmg_vcycle_internal(femol_gmg* g, const double* r, double* z, cudaStream_t st);
+int femol_gmg_vcycle_internal(femol_gmg* g, const double* r, double* z, cudaStream_t st, double* rz_out, double* red_ws,
+                              bool* rz_fused);
+int femol_gmg_iteration_hint(femol_gmg* g, int set);
 
 namespace {
 
-__device__ __forceinline__ int rz_cur(const double* sc) { return (((long long)sc[S_ITER]) & 1LL) ? S_RZ1 : S_RZ0; }
-__device__ __forceinline__ int rz_other(const double* sc) { return (((long long)sc[S_ITER]) & 1LL) ? S_RZ0 : S_RZ1; }
-
+// r.z lives in two slots: S_RZN (written by the V-cycle's last kernel, or by gpcg_dot) and S_RZO (the previous one,
+// copied by gpcg_update once every block has read S_RZN), so the captured launch sequence is static.
 // r = f - q ; rr = r.r ; ff = f.f
 __global__ void __launch_bounds__(VEC_THREADS)
 gpcg_init(int64_t n, const double* __restrict__ f, const double* __restrict__ q, double* __restrict__ r,
@@ -332,7 +333,7 @@ gpcg_dot(int64_t n, const double* __restrict__ r, const double* __restrict__ z, 
     __shared__ double s_red[32];
     double acc[1] = {0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc[0] += r[i] * z[i];
-    if (grid_sum_last<1>(acc, red_ws, red_ticket(red_ws), s_red)) sc[rz_cur(sc)] = acc[0];
+    if (grid_sum_last<1>(acc, red_ws, red_ticket(red_ws), s_red)) sc[S_RZN] = acc[0];
 }
 
 // u += alpha p ; r -= alpha q ; rr ; iteration counter (flips the r.z slot) ; convergence flag
@@ -341,7 +342,7 @@ gpcg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ 
             double* __restrict__ r, double* __restrict__ sc, double* __restrict__ red_ws) {
     if (sc[S_DONE] != 0.0) return;
     __shared__ double s_red[32];
-    const double rz = sc[rz_cur(sc)], pq = sc[S_PQ];
+    const double rz = sc[S_RZN], pq = sc[S_PQ];
     const double alpha = rz / pq;
     double acc[1] = {0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -352,6 +353,7 @@ gpcg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ 
     }
     if (grid_sum_last<1>(acc, red_ws, red_ticket(red_ws), s_red)) {
         sc[S_RR] = acc[0];
+        sc[S_RZO] = rz;
         sc[S_ITER] += 1.0;
         if (!(pq > 0.0) || !(acc[0] == acc[0])) sc[S_DONE] = 2.0;
         else if (acc[0] <= sc[S_TOL2]) sc[S_DONE] = 1.0;
@@ -362,7 +364,7 @@ gpcg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ 
 __global__ void __launch_bounds__(VEC_THREADS)
 gpcg_direction(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ sc, int first) {
     if (sc[S_DONE] != 0.0) return;
-    const double beta = first ? 0.0 : sc[rz_cur(sc)] / sc[rz_other(sc)];
+    const double beta = first ? 0.0 : sc[S_RZN] / sc[S_RZO];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = first ? z[i] : z[i] + beta * p[i];
 }
@@ -376,10 +378,13 @@ int gpcg_iteration(const GpcgCtx& c, cudaStream_t st) {
     if (rc != FEMOL_OK) return rc;
     gpcg_update<<<c.vgrid, VEC_THREADS, 0, st>>>(c.n, c.p, c.q, c.u, c.r, c.sc, c.red);
     FEMOL_LAUNCH_CHECK();
-    rc = femol_gmg_vcycle_internal(c.gmg, c.r, c.z, st);
+    bool rz_fused = false;
+    rc = femol_gmg_vcycle_internal(c.gmg, c.r, c.z, st, c.sc + S_RZN, c.red, &rz_fused);
     if (rc != FEMOL_OK) return rc;
-    gpcg_dot<<<c.vgrid, VEC_THREADS, 0, st>>>(c.n, c.r, c.z, c.sc, c.red);
-    FEMOL_LAUNCH_CHECK();
+    if (!rz_fused) {
+        gpcg_dot<<<c.vgrid, VEC_THREADS, 0, st>>>(c.n, c.r, c.z, c.sc, c.red);
+        FEMOL_LAUNCH_CHECK();
+    }
     gpcg_direction<<<c.vgrid, VEC_THREADS, 0, st>>>(c.n, c.z, c.p, c.sc, 0);
     FEMOL_LAUNCH_CHECK();
     return FEMOL_OK;
@@ -426,9 +431,10 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
         prev_true_rel = true_rel;
         if (total_iters >= max_iter) break;
         // z = V(r), rz, p = z
-        rc = femol_gmg_vcycle_internal(gmg, c.r, c.z, st);
+        bool rz_fused = false;
+        rc = femol_gmg_vcycle_internal(gmg, c.r, c.z, st, c.sc + S_RZN, c.red, &rz_fused);
         if (rc != FEMOL_OK) { cleanup(); return rc; }
-        gpcg_dot<<<c.vgrid, VEC_THREADS, 0, st>>>(n, c.r, c.z, c.sc, c.red);
+        if (!rz_fused) gpcg_dot<<<c.vgrid, VEC_THREADS, 0, st>>>(n, c.r, c.z, c.sc, c.red);
         gpcg_direction<<<c.vgrid, VEC_THREADS, 0, st>>>(n, c.z, c.p, c.sc, 1);
         FEMOL_LAUNCH_CHECK();
         if (use_graph && !exec) {  // capture one CG iteration (static launch sequence) once per solve
@@ -446,8 +452,14 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
             cudaGetLastError();  // a failed capture must not poison later launch checks
         }
         bool finished = false;
+        // iterations between two host reads of the convergence flag: the previous solve's count (minus a margin)
+        // first - consecutive SIMP iterations need almost the same number - then `batch` at a time; iterations
+        // launched after convergence return immediately in the CG kernels
+        int first_batch = restart == 0 ? femol_gmg_iteration_hint(gmg, -1) - 3 : batch;
         while (!finished && total_iters < max_iter) {
-            const int nb = (max_iter - total_iters) < batch ? (max_iter - total_iters) : batch;
+            int nb = first_batch > batch ? first_batch : batch;
+            first_batch = 0;
+            if (nb > max_iter - total_iters) nb = max_iter - total_iters;
             for (int it = 0; it < nb; ++it) {
                 if (exec) { FEMOL_CUDA_CHECK(cudaGraphLaunch(exec, st)); femol_count_launches(graph_kernels); }
                 else if ((rc = gpcg_iteration(c, st)) != FEMOL_OK) { cleanup(); return rc; }
@@ -461,6 +473,7 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
         if (status == FEMOL_S_BREAKDOWN || !finished) break;
     }
     cleanup();
+    femol_gmg_iteration_hint(gmg, total_iters);
     if (status == FEMOL_S_NOT_CONVERGED) {
         int rc = femol_apply_launch(plan, vals, u, c.q, nullptr, nullptr, nullptr, st);
         if (rc != FEMOL_OK) return rc;

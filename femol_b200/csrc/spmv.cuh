@@ -57,7 +57,9 @@ spmv_node_kernel(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, const int
                 const int da = (int)(r & 1);
                 const double mine = __ldg(&rhs[r]) - acc, theirs = __ldg(&rhs[r ^ 1]) - other;
                 const double2 d = __ldg(reinterpret_cast<const double2*>(dinv) + i * 2 + da);   // row da of the 2 x 2 block
-                y[r] = __ldg(&x[r]) + omega * (da == 0 ? d.x * mine + d.y * theirs : d.x * theirs + d.y * mine);
+                const double out = __ldg(&x[r]) + omega * (da == 0 ? d.x * mine + d.y * theirs : d.x * theirs + d.y * mine);
+                y[r] = out;
+                if (dot_out) dot[0] += out * __ldg(&rhs[r]);      // fused y . rhs (the r.z of preconditioned CG)
             }
         } else if (g == 0 && r < n_rows) {
             const double out = MODE == 1 ? __ldg(&rhs[r]) - acc : acc;
@@ -122,6 +124,8 @@ struct femol_epilogue {
     const double* rhs;   // r in modes 1, 2
     const double* dinv;  // [n_nodes][ND][ND] block-diagonal inverse, mode 2
     double omega;        // damping, mode 2
+    double* dot_out;     // mode 2, optional: dot_out[0] = y . rhs (deterministic grid sum, needs red_ws)
+    double* red_ws;
 };
 #define FEMOL_EPI_NONE 0      // y = K x
 #define FEMOL_EPI_RESIDUAL 1  // y = rhs - K x

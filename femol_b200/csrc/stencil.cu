@@ -225,6 +225,13 @@ stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int
                     }
                     acc[q][da] = __ldg(un + da) + omega * t;
                 }
+                if (dot_out) {      // fused y . rhs (the r.z of preconditioned CG)
+#pragma unroll
+                    for (int d = 0; d < ND; d += 2) {
+                        const double2 r2 = __ldg(reinterpret_cast<const double2*>(rhs + (size_t)n * ND + d));
+                        dot[0] = fma(acc[q][d], r2.x, dot[0]); dot[0] = fma(acc[q][d + 1], r2.y, dot[0]);
+                    }
+                }
             }
 #pragma unroll
             for (int d = 0; d < ND; d += 2) {
@@ -285,7 +292,7 @@ template <int ND>
 int launch_stencil_mode(femol_plan_t p, const femol_matrix_free* mf, const double* x, double* y, const double* dot_with,
                         double* dot_out, double* red_ws, const femol_epilogue& ep, cudaStream_t st) {
     if (ep.mode == FEMOL_EPI_RESIDUAL) return launch_stencil<ND, 1>(p, mf, x, y, nullptr, nullptr, red_ws, ep, st);
-    if (ep.mode == FEMOL_EPI_JACOBI) return launch_stencil<ND, 2>(p, mf, x, y, nullptr, nullptr, red_ws, ep, st);
+    if (ep.mode == FEMOL_EPI_JACOBI) return launch_stencil<ND, 2>(p, mf, x, y, nullptr, ep.dot_out, ep.red_ws, ep, st);
     return launch_stencil<ND, 0>(p, mf, x, y, dot_with, dot_out, red_ws, ep, st);
 }
 
@@ -300,7 +307,7 @@ static inline const femol_matrix_free* stencil_for(femol_plan_t p, const double*
 
 int femol_apply_launch(femol_plan_t p, const double* vals, const double* x, double* y, const double* dot_with,
                        double* dot_out, double* red_ws, cudaStream_t st) {
-    const femol_epilogue none = {FEMOL_EPI_NONE, nullptr, nullptr, 0.0};
+    const femol_epilogue none = {FEMOL_EPI_NONE, nullptr, nullptr, 0.0, nullptr, nullptr};
     if (const femol_matrix_free* mf = stencil_for(p, vals)) {
         if (p->ndof == 2) return launch_stencil_mode<2>(p, mf, x, y, dot_with, dot_out, red_ws, none, st);
         return launch_stencil_mode<6>(p, mf, x, y, dot_with, dot_out, red_ws, none, st);
@@ -321,7 +328,7 @@ int femol_apply_epilogue_launch(femol_plan_t p, const double* vals, const double
         if (p->ndof == 2) return spmv_node_launch<2, 1>(p, vals, x, y, nullptr, nullptr, nullptr, st, ep.rhs);
         if (p->ndof == 6) return spmv_node_launch<6, 1>(p, vals, x, y, nullptr, nullptr, nullptr, st, ep.rhs);
     } else if (ep.mode == FEMOL_EPI_JACOBI && p->ndof == 2) {
-        return spmv_node_launch<2, 2>(p, vals, x, y, nullptr, nullptr, nullptr, st, ep.rhs, ep.dinv, ep.omega);
+        return spmv_node_launch<2, 2>(p, vals, x, y, nullptr, ep.dot_out, ep.red_ws, st, ep.rhs, ep.dinv, ep.omega);
     }
     femol_set_error("femol_apply_epilogue_launch: mode %d not available for ndof %d", ep.mode, p->ndof);
     return FEMOL_E_ARG;
@@ -355,7 +362,7 @@ extern "C" int femol_apply_epilogue(femol_plan_t p, const double* vals, const do
     FEMOL_REQUIRE(p && vals && x && y && x != y, "femol_apply_epilogue: null or aliased argument");
     FEMOL_REQUIRE(mode >= 0 && mode <= 2 && (mode == 0 || rhs) && (mode != 2 || dinv), "femol_apply_epilogue: bad mode / missing operand");
     FEMOL_REQUIRE(mode != 2 || femol_apply_has_jacobi(p, vals), "femol_apply_epilogue: mode 2 needs ndof = 2 or the matrix-free operator");
-    const femol_epilogue ep = {mode, rhs, dinv, omega};
+    const femol_epilogue ep = {mode, rhs, dinv, omega, nullptr, nullptr};
     return femol_apply_epilogue_launch(p, vals, x, y, ep, (cudaStream_t)stream);
 }
 
