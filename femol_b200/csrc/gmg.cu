@@ -36,6 +36,7 @@ struct Level {
     uint8_t* fixed;     // node masks (level 0: borrowed, may be NULL)
     double* ke;         // [n_elem][S][S] (levels >= 1)
     double* vals;       // CSR values (levels >= 1; level 0: set per setup)
+    float* vals32;      // the same values in single precision (regular levels >= 1 of the mixed-precision V-cycle) or NULL
     double* dinv;       // [n_nodes][ND][ND]
     double *r, *e, *t;  // work vectors (level 0: r, e supplied by the caller through vcycle)
 };
@@ -55,6 +56,7 @@ struct femol_gmg {
     int solo_from;       // ... first level CTA 0 handles alone, ...
     int cluster_size;    // ... CTAs per cluster (0: unavailable)
     int hint_iters;      // CG iterations of the previous solve with this hierarchy (sizes the first batch)
+    bool f32_levels;     // coarse-level operators stored in single precision for the smoother products (FEMOL_GMG_F32)
 };
 
 namespace {
@@ -298,6 +300,10 @@ prolong_add_kernel(int64_t nxf, int64_t nyf, int64_t nxc, const uint8_t* __restr
             out[t * ND + d] = ef[t * ND + d] + v;
         }
     }
+}
+
+__global__ void __launch_bounds__(256) to_float_kernel(int64_t n, const double* __restrict__ a, float* __restrict__ b) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) b[i] = (float)a[i];
 }
 
 // ---- smoother ------------------------------------------------------------------------------------------------------
@@ -824,7 +830,9 @@ int smooth(femol_gmg* g, int l, const double* r, double* e, bool zero_start, cud
             jacobi_kernel<ND, true><<<grid, 256, 0, st>>>(L.n_nodes, g->omega, L.dinv, r, nullptr, e);
             FEMOL_LAUNCH_CHECK();
         } else {
-            int rc = femol_apply_launch(L.plan, L.vals, e, L.t, nullptr, nullptr, nullptr, st);
+            const femol_epilogue none = {FEMOL_EPI_NONE, nullptr, nullptr, 0.0, nullptr, nullptr};
+            int rc = L.vals32 ? femol_spmv_f32_epilogue_launch(L.plan, L.vals32, e, L.t, none, st)
+                              : femol_apply_launch(L.plan, L.vals, e, L.t, nullptr, nullptr, nullptr, st);
             if (rc != FEMOL_OK) return rc;
             jacobi_kernel<ND, false><<<grid, 256, 0, st>>>(L.n_nodes, g->omega, L.dinv, r, L.t, e);
             FEMOL_LAUNCH_CHECK();
@@ -864,7 +872,8 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, boo
             FEMOL_LAUNCH_CHECK();
         }
         const femol_epilogue res = {FEMOL_EPI_RESIDUAL, r, nullptr, 0.0, nullptr, nullptr};
-        rc = femol_apply_epilogue_launch(L.plan, L.vals, e, L.t, res, st);
+        rc = L.vals32 ? femol_spmv_f32_epilogue_launch(L.plan, L.vals32, e, L.t, res, st)
+                      : femol_apply_epilogue_launch(L.plan, L.vals, e, L.t, res, st);
         if (rc != FEMOL_OK) return rc;
         const bool coarse_regular = l + 1 != g->n_levels - 1;   // every smoothing level starts from omega Dinv r
         restrict_kernel<ND><<<grid_for(C.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, C.ny, L.fixed, C.fixed, L.t, C.r,
@@ -878,7 +887,8 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, boo
             // level 0 inside CG: the last kernel of the V-cycle also delivers r . z
             const femol_epilogue jac = {FEMOL_EPI_JACOBI, r, L.dinv, g->omega, rz_out, red_ws};
             if (rz_out && rz_fused) *rz_fused = true;
-            return femol_apply_epilogue_launch(L.plan, L.vals, L.t, e, jac, st);
+            return L.vals32 ? femol_spmv_f32_epilogue_launch(L.plan, L.vals32, L.t, e, jac, st)
+                            : femol_apply_epilogue_launch(L.plan, L.vals, L.t, e, jac, st);
         }
         prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e, e);
         FEMOL_LAUNCH_CHECK();
@@ -922,7 +932,7 @@ extern "C" int femol_gmg_destroy(femol_gmg* g) {
         Level& L = g->lv[l];
         if (l > 0) {
             femol_plan_destroy(L.plan);
-            cudaFree(L.fixed); cudaFree(L.ke); cudaFree(L.vals); cudaFree(L.r); cudaFree(L.e);
+            cudaFree(L.fixed); cudaFree(L.ke); cudaFree(L.vals); cudaFree(L.vals32); cudaFree(L.r); cudaFree(L.e);
         }
         cudaFree(L.dinv); cudaFree(L.t);
     }
@@ -943,6 +953,10 @@ extern "C" int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t f
     femol_gmg* g = new femol_gmg();
     memset(g, 0, sizeof(*g));
     g->nd = ndof; g->nu = nu > 0 ? nu : 2; g->omega = omega > 0 ? omega : 0.6;
+    {   // mixed precision: only the stored coarse operators are rounded, every vector and sum stays in double
+        const char* env = getenv("FEMOL_GMG_F32");
+        g->f32_levels = g->nu == 1 && !(env && atoi(env) == 0);
+    }
     auto fail = [&](int code) { femol_gmg_destroy(g); return code; };
 #define GCHECK(expr)                                                                              \
     do {                                                                                          \
@@ -977,6 +991,8 @@ extern "C" int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t f
             GCHECK(cudaGetLastError());
             GCHECK(cudaMalloc(&L.ke, L.n_elem * S2 * sizeof(double)));
             GCHECK(cudaMalloc(&L.vals, L.plan->nnz * sizeof(double)));
+            L.vals32 = nullptr;
+            if (g->f32_levels) GCHECK(cudaMalloc(&L.vals32, L.plan->nnz * sizeof(float)));
             GCHECK(cudaMalloc(&L.r, L.n * sizeof(double)));
             GCHECK(cudaMalloc(&L.e, L.n * sizeof(double)));
         }
@@ -1067,6 +1083,10 @@ extern "C" int femol_gmg_setup(femol_gmg* g, const double* e_base, const double*
         FEMOL_LAUNCH_CHECK();
         int rc = femol_assemble(C.plan, C.ke, 1, nullptr, 0, nullptr, 1.0, C.fixed, nullptr, C.vals, st);
         if (rc != FEMOL_OK) return rc;
+        if (C.vals32) {
+            to_float_kernel<<<grid_for(C.plan->nnz), 256, 0, st>>>(C.plan->nnz, C.vals, C.vals32);
+            FEMOL_LAUNCH_CHECK();
+        }
     }
     for (int l = 0; l < g->n_levels - 1; ++l) {
         int rc = femol_precond_setup(g->lv[l].plan, g->lv[l].vals, FEMOL_PRECOND_BLOCK_JACOBI, g->lv[l].dinv, st);

@@ -60,6 +60,21 @@ int femol_spmv_launch(femol_plan_t p, const double* vals, const double* x, doubl
     return rc;
 }
 
+int femol_spmv_f32_epilogue_launch(femol_plan_t p, const float* vals32, const double* x, double* y, const femol_epilogue& ep,
+                                   cudaStream_t st) {
+    if (ep.mode == FEMOL_EPI_RESIDUAL) {
+        if (p->ndof == 2) return spmv_node_launch<2, 1, float>(p, vals32, x, y, nullptr, nullptr, nullptr, st, ep.rhs);
+        if (p->ndof == 6) return spmv_node_launch<6, 1, float>(p, vals32, x, y, nullptr, nullptr, nullptr, st, ep.rhs);
+    } else if (ep.mode == FEMOL_EPI_JACOBI && p->ndof == 2) {
+        return spmv_node_launch<2, 2, float>(p, vals32, x, y, nullptr, ep.dot_out, ep.red_ws, st, ep.rhs, ep.dinv, ep.omega);
+    } else if (ep.mode == FEMOL_EPI_NONE) {
+        if (p->ndof == 2) return spmv_node_launch<2, 0, float>(p, vals32, x, y, nullptr, nullptr, nullptr, st);
+        if (p->ndof == 6) return spmv_node_launch<6, 0, float>(p, vals32, x, y, nullptr, nullptr, nullptr, st);
+    }
+    femol_set_error("femol_spmv_f32: mode %d not available for ndof %d", ep.mode, p->ndof);
+    return FEMOL_E_ARG;
+}
+
 extern "C" int femol_spmv(femol_plan_t p, const double* vals, const double* x, double* y, void* stream) {
     FEMOL_REQUIRE(p && vals && x && y, "femol_spmv: null argument");
     return femol_spmv_launch(p, vals, x, y, nullptr, nullptr, nullptr, (cudaStream_t)stream);

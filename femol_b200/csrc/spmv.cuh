@@ -11,10 +11,16 @@ size_t femol_l2_persist_bytes();
 // Optional fused dot product: dot_out[0] = sum_r y[r] * dot_with[r] (deterministic grid reduction).
 // MODE (femol_epilogue): 0  y = K x;  1  y = rhs - K x;  2  y = x + omega Dinv (rhs - K x)  (ND = 2 only: the two
 // rows of a node sit in neighbouring lane groups of one warp, so the 2 x 2 block product is one shuffle away).
-template <int ND, int G, int MODE = 0>
+// VT: storage type of the matrix values (double; float for the mixed-precision multigrid levels - the arithmetic
+// stays in double).
+template <typename VT> struct femol_pair;
+template <> struct femol_pair<double> { typedef double2 type; };
+template <> struct femol_pair<float> { typedef float2 type; };
+
+template <int ND, int G, int MODE = 0, typename VT = double>
 __global__ void __launch_bounds__(256)
 spmv_node_kernel(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx,
-                 const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                 const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
                  const double* __restrict__ dot_with, double* __restrict__ dot_out, double* __restrict__ red_ws,
                  const double* __restrict__ rhs = nullptr, const double* __restrict__ dinv = nullptr, double omega = 0.0) {
     static_assert(MODE != 2 || (ND == 2 && 32 % (2 * G) == 0), "fused Jacobi needs both rows of a node in one warp");
@@ -37,15 +43,16 @@ spmv_node_kernel(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, const int
             const int pb = __ldg(&adj_ptr[i]);
             const int len = __ldg(&adj_ptr[i + 1]) - pb;
             const int64_t base2 = ((int64_t)ND * ND * pb + (int64_t)da * len * ND) >> 1;
-            const double2* __restrict__ v2 = reinterpret_cast<const double2*>(vals) + base2;
+            typedef typename femol_pair<VT>::type VT2;
+            const VT2* __restrict__ v2 = reinterpret_cast<const VT2*>(vals) + base2;
             const int n2 = len * H;
             for (int c = g; c < n2; c += G) {
                 const int k = c / H, h = c - k * H;
                 const int32_t j = __ldg(&adj_idx[pb + k]);
-                const double2 a = __ldcs(&v2[c]);
+                const VT2 a = __ldcs(&v2[c]);
                 const double2 b = __ldg(&x2[(int64_t)j * H + h]);
-                acc += a.x * b.x;
-                acc += a.y * b.y;
+                acc += (double)a.x * b.x;
+                acc += (double)a.y * b.y;
             }
         }
 #pragma unroll
@@ -73,8 +80,8 @@ spmv_node_kernel(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, const int
     }
 }
 
-template <int ND, int MODE = 0>
-int spmv_node_launch(femol_plan_t p, const double* vals, const double* x, double* y, const double* dot_with,
+template <int ND, int MODE = 0, typename VT = double>
+int spmv_node_launch(femol_plan_t p, const VT* vals, const double* x, double* y, const double* dot_with,
                      double* dot_out, double* red_ws, cudaStream_t st, const double* rhs = nullptr,
                      const double* dinv = nullptr, double omega = 0.0) {
     constexpr int G = ND == 2 ? 4 : 8;
@@ -101,13 +108,13 @@ int spmv_node_launch(femol_plan_t p, const double* vals, const double* x, double
         attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cfg.attrs = attr; cfg.numAttrs = 1;
         const int64_t nn = p->n_nodes;
-        FEMOL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, spmv_node_kernel<ND, G, MODE>, nn, (const int32_t*)p->adj_ptr,
+        FEMOL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, spmv_node_kernel<ND, G, MODE, VT>, nn, (const int32_t*)p->adj_ptr,
                                             (const int32_t*)p->adj_idx, vals, x, y, dot_with, dot_out, red_ws, rhs, dinv,
                                             omega));
         femol_count_launch();
         return FEMOL_OK;
     }
-    spmv_node_kernel<ND, G, MODE><<<(int)blocks, 256, 0, st>>>(p->n_nodes, p->adj_ptr, p->adj_idx, vals, x, y, dot_with,
+    spmv_node_kernel<ND, G, MODE, VT><<<(int)blocks, 256, 0, st>>>(p->n_nodes, p->adj_ptr, p->adj_idx, vals, x, y, dot_with,
                                                                 dot_out, red_ws, rhs, dinv, omega);
     FEMOL_LAUNCH_CHECK();
     return FEMOL_OK;
@@ -134,3 +141,6 @@ struct femol_epilogue {
 bool femol_apply_has_jacobi(femol_plan_t p, const double* vals);
 int femol_apply_epilogue_launch(femol_plan_t p, const double* vals, const double* x, double* y, const femol_epilogue& ep,
                                 cudaStream_t st);
+// CSR product from single-precision values (mixed-precision multigrid levels): modes 1 and, for ndof = 2, 2
+int femol_spmv_f32_epilogue_launch(femol_plan_t p, const float* vals32, const double* x, double* y, const femol_epilogue& ep,
+                                   cudaStream_t st);
