@@ -222,55 +222,69 @@ coarsen_elements(int64_t nxf, int64_t nyf, int64_t nxc, int64_t nyc, const doubl
 }
 
 // ---- transfer operators ---------------------------------------------------------------------------------------
-// r_c = P^T r_f   (fine fixed dofs do not restrict; coarse fixed dofs receive 0)
+// 1-D weight of fine node c + dc in the restriction onto the coarse node centred at fine index c (n fine cells):
+// the transpose of cmap1d.  c is even except for the last node of an odd grid, which has no half-weight neighbours.
+__device__ __forceinline__ double rweight1d(int c, int dc, int n) {
+    if (dc == 0) return 1.0;
+    const int i = c + dc;
+    if (i < 0 || i > n || (c & 1)) return 0.0;
+    if (dc == 1 && i == n) return 0.0;      // i is the (odd) last node: it is a coarse node of its own
+    return 0.5;
+}
+
+// r_c = P^T r_f   (fine fixed dofs do not restrict; coarse fixed dofs receive 0); with dinv_c also the coarse
+// level's first sweep e_c = omega Dinv_c r_c.  All nine fine loads of a thread are issued before they are used
+// (the mask no longer gates the value load: the first version was a chain of dependent L2 round trips).
 template <int ND>
 __global__ void __launch_bounds__(256)
-restrict_kernel(int64_t nxf, int64_t nyf, int64_t nxc, int64_t nyc, const uint8_t* __restrict__ ff,
+restrict_kernel(int64_t nxf64, int64_t nyf64, int64_t nxc64, int64_t nyc64, const uint8_t* __restrict__ ff,
                 const uint8_t* __restrict__ fc, const double* __restrict__ rf, double* __restrict__ rc,
                 const double* __restrict__ dinv_c, double omega, double* __restrict__ ec) {
-    const int64_t nn = (nxc + 1) * (nyc + 1);
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nn; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t J = t / (nxc + 1), I = t - J * (nxc + 1);
-        const int64_t ic = min(2 * I, nxf), jc = min(2 * J, nyf);
+    const int nxf = (int)nxf64, nyf = (int)nyf64, nxc = (int)nxc64, nyc = (int)nyc64;
+    const int nn = (nxc + 1) * (nyc + 1);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += gridDim.x * blockDim.x) {
+        const int J = t / (nxc + 1), I = t - J * (nxc + 1);
+        const int ic = min(2 * I, nxf), jc = min(2 * J, nyf);
         double acc[ND];
 #pragma unroll
         for (int d = 0; d < ND; ++d) acc[d] = 0.0;
-        for (int dj = -1; dj <= 1; ++dj) {
-            const int64_t j = jc + dj;
-            if (j < 0 || j > nyf) continue;
-            int64_t J0, J1; double v0, v1;
-            cmap1d(j, nyf, J0, v0, J1, v1);
-            const double wy = (J0 == J ? v0 : 0.0) + (J1 == J && v1 != 0.0 ? v1 : 0.0);
-            if (wy == 0.0) continue;
-            for (int di = -1; di <= 1; ++di) {
-                const int64_t i = ic + di;
-                if (i < 0 || i > nxf) continue;
-                int64_t I0, I1; double u0, u1;
-                cmap1d(i, nxf, I0, u0, I1, u1);
-                const double wx = (I0 == I ? u0 : 0.0) + (I1 == I && u1 != 0.0 ? u1 : 0.0);
-                if (wx == 0.0) continue;
-                const int64_t nf = j * (nxf + 1) + i;
-                const uint32_t fm = ff ? ff[nf] : 0u;
-                const double w = wx * wy;
 #pragma unroll
-                for (int d = 0; d < ND; ++d)
-                    if (!((fm >> d) & 1u)) acc[d] += w * rf[nf * ND + d];
+        for (int dj = -1; dj <= 1; ++dj) {
+            const double wy = rweight1d(jc, dj, nyf);
+#pragma unroll
+            for (int di = -1; di <= 1; ++di) {
+                const double w = wy * rweight1d(ic, di, nxf);
+                if (w == 0.0) continue;
+                const int nf = (jc + dj) * (nxf + 1) + ic + di;
+                const uint32_t fm = ff ? __ldg(&ff[nf]) : 0u;
+#pragma unroll
+                for (int d = 0; d < ND; d += 2) {
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(rf + (size_t)nf * ND + d));
+                    acc[d] += ((fm >> d) & 1u) ? 0.0 : w * v.x;
+                    acc[d + 1] += ((fm >> (d + 1)) & 1u) ? 0.0 : w * v.y;
+                }
             }
         }
         const uint32_t cm = fc ? fc[t] : 0u;
 #pragma unroll
-        for (int d = 0; d < ND; ++d) {
+        for (int d = 0; d < ND; d += 2) {
             if ((cm >> d) & 1u) acc[d] = 0.0;
-            rc[t * ND + d] = acc[d];
+            if ((cm >> (d + 1)) & 1u) acc[d + 1] = 0.0;
+            *reinterpret_cast<double2*>(rc + (size_t)t * ND + d) = make_double2(acc[d], acc[d + 1]);
         }
         if (dinv_c) {   // the coarse level's first smoothing sweep from a zero guess: e_c = omega Dinv r_c
-            const double* B = dinv_c + t * ND * ND;
+            const double* B = dinv_c + (size_t)t * ND * ND;
 #pragma unroll
-            for (int a = 0; a < ND; ++a) {
-                double sacc = 0.0;
+            for (int a = 0; a < ND; a += 2) {
+                double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                for (int b = 0; b < ND; ++b) sacc += __ldg(&B[a * ND + b]) * acc[b];
-                ec[t * ND + a] = omega * sacc;
+                for (int b = 0; b < ND; b += 2) {
+                    const double2 b0 = __ldg(reinterpret_cast<const double2*>(B + a * ND + b));
+                    const double2 b1 = __ldg(reinterpret_cast<const double2*>(B + (a + 1) * ND + b));
+                    s0 += b0.x * acc[b] + b0.y * acc[b + 1];
+                    s1 += b1.x * acc[b] + b1.y * acc[b + 1];
+                }
+                *reinterpret_cast<double2*>(ec + (size_t)t * ND + a) = make_double2(omega * s0, omega * s1);
             }
         }
     }
@@ -279,25 +293,31 @@ restrict_kernel(int64_t nxf, int64_t nyf, int64_t nxc, int64_t nyc, const uint8_
 // out = e_f + P e_c   (fixed fine dofs copied; out may alias e_f)
 template <int ND>
 __global__ void __launch_bounds__(256)
-prolong_add_kernel(int64_t nxf, int64_t nyf, int64_t nxc, const uint8_t* __restrict__ ff,
+prolong_add_kernel(int64_t nxf64, int64_t nyf64, int64_t nxc64, const uint8_t* __restrict__ ff,
                    const double* __restrict__ ec, const double* ef, double* out) {
-    const int64_t nn = (nxf + 1) * (nyf + 1);
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nn; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = t / (nxf + 1), i = t - j * (nxf + 1);
+    const int nxf = (int)nxf64, nyf = (int)nyf64, nxc = (int)nxc64;
+    const int nn = (nxf + 1) * (nyf + 1);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += gridDim.x * blockDim.x) {
+        const int j = t / (nxf + 1), i = t - j * (nxf + 1);
         int64_t I0, I1, J0, J1; double u0, u1, v0, v1;
-        cmap1d(i, nxf, I0, u0, I1, u1);
+        cmap1d(i, nxf, I0, u0, I1, u1);      // I1 = I0 (weight 0) when the node coincides with a coarse node
         cmap1d(j, nyf, J0, v0, J1, v1);
-        const uint32_t fm = ff ? ff[t] : 0u;
-        const int64_t c00 = J0 * (nxc + 1) + I0, c10 = J0 * (nxc + 1) + I1, c01 = J1 * (nxc + 1) + I0, c11 = J1 * (nxc + 1) + I1;
+        const uint32_t fm = ff ? __ldg(&ff[t]) : 0u;
+        const int c00 = (int)J0 * (nxc + 1) + (int)I0, c10 = (int)J0 * (nxc + 1) + (int)I1;
+        const int c01 = (int)J1 * (nxc + 1) + (int)I0, c11 = (int)J1 * (nxc + 1) + (int)I1;
+        const double w00 = u0 * v0, w10 = u1 * v0, w01 = u0 * v1, w11 = u1 * v1;
 #pragma unroll
-        for (int d = 0; d < ND; ++d) {
-            double v = 0.0;
-            if (!((fm >> d) & 1u)) {
-                v = u0 * v0 * ec[c00 * ND + d];
-                if (u1 != 0.0) v += u1 * v0 * ec[c10 * ND + d];
-                if (v1 != 0.0) { v += u0 * v1 * ec[c01 * ND + d]; if (u1 != 0.0) v += u1 * v1 * ec[c11 * ND + d]; }
-            }
-            out[t * ND + d] = ef[t * ND + d] + v;
+        for (int d = 0; d < ND; d += 2) {
+            const double2 a00 = __ldg(reinterpret_cast<const double2*>(ec + (size_t)c00 * ND + d));
+            const double2 a10 = __ldg(reinterpret_cast<const double2*>(ec + (size_t)c10 * ND + d));
+            const double2 a01 = __ldg(reinterpret_cast<const double2*>(ec + (size_t)c01 * ND + d));
+            const double2 a11 = __ldg(reinterpret_cast<const double2*>(ec + (size_t)c11 * ND + d));
+            double2 o = *reinterpret_cast<const double2*>(ef + (size_t)t * ND + d);
+            const double vx = w00 * a00.x + w10 * a10.x + w01 * a01.x + w11 * a11.x;
+            const double vy = w00 * a00.y + w10 * a10.y + w01 * a01.y + w11 * a11.y;
+            if (!((fm >> d) & 1u)) o.x += vx;
+            if (!((fm >> (d + 1)) & 1u)) o.y += vy;
+            *reinterpret_cast<double2*>(out + (size_t)t * ND + d) = o;
         }
     }
 }
@@ -911,6 +931,14 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, boo
 
 }  // namespace
 
+// nu = 1: the caller may compute the V-cycle's first sweep z = omega Dinv r itself (level-0 block inverse) and
+// pass presmoothed = true to femol_gmg_vcycle_internal
+bool femol_gmg_first_sweep(femol_gmg* g, const double** dinv, double* omega) {
+    if (g->nu != 1 || g->n_levels < 2) return false;
+    *dinv = g->lv[0].dinv; *omega = g->omega;
+    return true;
+}
+
 // remembers the CG iteration count of the last solve (set >= 0 stores, set < 0 only reads)
 int femol_gmg_iteration_hint(femol_gmg* g, int set) {
     if (set >= 0) g->hint_iters = set;
@@ -920,10 +948,10 @@ int femol_gmg_iteration_hint(femol_gmg* g, int set) {
 // z = V(r).  With rz_out (device scalar) the product r . z is requested as well; *rz_fused tells whether the V-cycle's
 // last kernel delivered it (otherwise the caller computes it).
 int femol_gmg_vcycle_internal(femol_gmg* g, const double* r, double* z, cudaStream_t st, double* rz_out, double* red_ws,
-                              bool* rz_fused) {
+                              bool* rz_fused, bool presmoothed) {
     if (rz_fused) *rz_fused = false;
-    return g->nd == 2 ? vcycle<2>(g, 0, r, z, st, false, rz_out, red_ws, rz_fused)
-                      : vcycle<6>(g, 0, r, z, st, false, rz_out, red_ws, rz_fused);
+    return g->nd == 2 ? vcycle<2>(g, 0, r, z, st, presmoothed, rz_out, red_ws, rz_fused)
+                      : vcycle<6>(g, 0, r, z, st, presmoothed, rz_out, red_ws, rz_fused);
 }
 
 extern "C" int femol_gmg_destroy(femol_gmg* g) {
@@ -1111,5 +1139,5 @@ extern "C" int femol_gmg_info(femol_gmg* g, int64_t* h_info /* [0]=levels, then 
 // z = V-cycle(r): one application of the preconditioner (exposed for tests and for LOBPCG)
 extern "C" int femol_gmg_apply(femol_gmg* g, const double* r, double* z, void* stream) {
     FEMOL_REQUIRE(g && r && z, "femol_gmg_apply: null argument");
-    return femol_gmg_vcycle_internal(g, r, z, (cudaStream_t)stream, nullptr, nullptr, nullptr);
+    return femol_gmg_vcycle_internal(g, r, z, (cudaStream_t)stream, nullptr, nullptr, nullptr, false);
 }

@@ -299,7 +299,8 @@ extern "C" int femol_pcg(femol_plan_t p, const double* vals, const double* f, do
 #include <stdlib.h>
 struct femol_gmg;
 int femol_gmg_vcycle_internal(femol_gmg* g, const double* r, double* z, cudaStream_t st, double* rz_out, double* red_ws,
-                              bool* rz_fused);
+                              bool* rz_fused, bool presmoothed);
+bool femol_gmg_first_sweep(femol_gmg* g, const double** dinv, double* omega);
 int femol_gmg_iteration_hint(femol_gmg* g, int set);
 
 namespace {
@@ -336,20 +337,57 @@ gpcg_dot(int64_t n, const double* __restrict__ r, const double* __restrict__ z, 
     if (grid_sum_last<1>(acc, red_ws, red_ticket(red_ws), s_red)) sc[S_RZN] = acc[0];
 }
 
-// u += alpha p ; r -= alpha q ; rr ; iteration counter (flips the r.z slot) ; convergence flag
+// u += alpha p ; r -= alpha q ; rr ; iteration counter ; convergence flag.  ND > 0: one thread per node, which also
+// writes the V-cycle's first smoothing sweep z = omega Dinv r (the multigrid then starts from it: one kernel and
+// one pass over r less per iteration).
+template <int ND>
 __global__ void __launch_bounds__(VEC_THREADS)
 gpcg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ u,
-            double* __restrict__ r, double* __restrict__ sc, double* __restrict__ red_ws) {
+            double* __restrict__ r, double* __restrict__ sc, double* __restrict__ red_ws,
+            const double* __restrict__ dinv, double omega, double* __restrict__ z) {
     if (sc[S_DONE] != 0.0) return;
     __shared__ double s_red[32];
     const double rz = sc[S_RZN], pq = sc[S_PQ];
     const double alpha = rz / pq;
     double acc[1] = {0.0};
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        u[i] += alpha * p[i];
-        const double rv = r[i] - alpha * q[i];
-        r[i] = rv;
-        acc[0] += rv * rv;
+    if (ND == 0) {
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+            u[i] += alpha * p[i];
+            const double rv = r[i] - alpha * q[i];
+            r[i] = rv;
+            acc[0] += rv * rv;
+        }
+    } else {
+        constexpr int NDD = ND > 0 ? ND : 2;
+        const int64_t n_nodes = n / NDD;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+            double rv[NDD];
+#pragma unroll
+            for (int d = 0; d < NDD; d += 2) {
+                const int64_t o = i * NDD + d;
+                const double2 p2 = *reinterpret_cast<const double2*>(p + o), q2 = *reinterpret_cast<const double2*>(q + o);
+                double2 u2 = *reinterpret_cast<double2*>(u + o), r2 = *reinterpret_cast<double2*>(r + o);
+                u2.x += alpha * p2.x; u2.y += alpha * p2.y;
+                r2.x -= alpha * q2.x; r2.y -= alpha * q2.y;
+                *reinterpret_cast<double2*>(u + o) = u2;
+                *reinterpret_cast<double2*>(r + o) = r2;
+                rv[d] = r2.x; rv[d + 1] = r2.y;
+                acc[0] += r2.x * r2.x + r2.y * r2.y;
+            }
+            const double* B = dinv + i * NDD * NDD;
+#pragma unroll
+            for (int a = 0; a < NDD; a += 2) {
+                double z0 = 0.0, z1 = 0.0;
+#pragma unroll
+                for (int b = 0; b < NDD; b += 2) {
+                    const double2 b0 = __ldg(reinterpret_cast<const double2*>(B + a * NDD + b));
+                    const double2 b1 = __ldg(reinterpret_cast<const double2*>(B + (a + 1) * NDD + b));
+                    z0 += b0.x * rv[b] + b0.y * rv[b + 1];
+                    z1 += b1.x * rv[b] + b1.y * rv[b + 1];
+                }
+                *reinterpret_cast<double2*>(z + i * NDD + a) = make_double2(omega * z0, omega * z1);
+            }
+        }
     }
     if (grid_sum_last<1>(acc, red_ws, red_ticket(red_ws), s_red)) {
         sc[S_RR] = acc[0];
@@ -371,15 +409,21 @@ gpcg_direction(int64_t n, const double* __restrict__ z, double* __restrict__ p, 
 
 struct GpcgCtx {
     femol_plan_t plan; femol_gmg* gmg; const double* vals; double *u, *r, *p, *q, *z, *sc, *red; int64_t n; int vgrid;
+    const double* dinv0; double omega0; bool first_sweep_fused; int ngrid;
 };
 
 int gpcg_iteration(const GpcgCtx& c, cudaStream_t st) {
     int rc = femol_apply_launch(c.plan, c.vals, c.p, c.q, c.p, c.sc + S_PQ, c.red, st);
     if (rc != FEMOL_OK) return rc;
-    gpcg_update<<<c.vgrid, VEC_THREADS, 0, st>>>(c.n, c.p, c.q, c.u, c.r, c.sc, c.red);
+    if (c.first_sweep_fused && c.plan->ndof == 2)
+        gpcg_update<2><<<c.ngrid, VEC_THREADS, 0, st>>>(c.n, c.p, c.q, c.u, c.r, c.sc, c.red, c.dinv0, c.omega0, c.z);
+    else if (c.first_sweep_fused && c.plan->ndof == 6)
+        gpcg_update<6><<<c.ngrid, VEC_THREADS, 0, st>>>(c.n, c.p, c.q, c.u, c.r, c.sc, c.red, c.dinv0, c.omega0, c.z);
+    else
+        gpcg_update<0><<<c.vgrid, VEC_THREADS, 0, st>>>(c.n, c.p, c.q, c.u, c.r, c.sc, c.red, nullptr, 0.0, nullptr);
     FEMOL_LAUNCH_CHECK();
     bool rz_fused = false;
-    rc = femol_gmg_vcycle_internal(c.gmg, c.r, c.z, st, c.sc + S_RZN, c.red, &rz_fused);
+    rc = femol_gmg_vcycle_internal(c.gmg, c.r, c.z, st, c.sc + S_RZN, c.red, &rz_fused, c.first_sweep_fused);
     if (rc != FEMOL_OK) return rc;
     if (!rz_fused) {
         gpcg_dot<<<c.vgrid, VEC_THREADS, 0, st>>>(c.n, c.r, c.z, c.sc, c.red);
@@ -407,6 +451,8 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
     c.plan = plan; c.gmg = gmg; c.vals = vals; c.u = u; c.n = n;
     c.r = ws; c.p = c.r + n; c.q = c.p + n; c.z = c.q + n; c.sc = c.z + n; c.red = c.sc + S_NSLOT;
     c.vgrid = femol_grid_for(n, VEC_THREADS, plan->sm_count, 8);
+    c.ngrid = femol_grid_for(plan->n_nodes, VEC_THREADS, plan->sm_count, 8);
+    c.first_sweep_fused = femol_gmg_first_sweep(gmg, &c.dinv0, &c.omega0) && (plan->ndof == 2 || plan->ndof == 6);
     FEMOL_CUDA_CHECK(cudaMemsetAsync(c.sc, 0, (S_NSLOT + FEMOL_RED_WS_DOUBLES) * sizeof(double), st));
     double h_sc[S_NSLOT];
     int total_iters = 0, status = FEMOL_S_NOT_CONVERGED;
@@ -432,7 +478,7 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
         if (total_iters >= max_iter) break;
         // z = V(r), rz, p = z
         bool rz_fused = false;
-        rc = femol_gmg_vcycle_internal(gmg, c.r, c.z, st, c.sc + S_RZN, c.red, &rz_fused);
+        rc = femol_gmg_vcycle_internal(gmg, c.r, c.z, st, c.sc + S_RZN, c.red, &rz_fused, false);
         if (rc != FEMOL_OK) { cleanup(); return rc; }
         if (!rz_fused) gpcg_dot<<<c.vgrid, VEC_THREADS, 0, st>>>(n, c.r, c.z, c.sc, c.red);
         gpcg_direction<<<c.vgrid, VEC_THREADS, 0, st>>>(n, c.z, c.p, c.sc, 1);

@@ -40,6 +40,15 @@ def main():
                  len(mid) // steps, sum(mid) / 1e3 / steps, len(big) // steps, sum(g for g, _ in big) / 1e3 / steps))
         for g, n in sorted(big, reverse=True)[:12]:
             print('   gap %8.1f us before %s' % (g, n[:90]))
+    # per-launch durations of the multilevel kernels (one cluster of values per multigrid level)
+    per = {}
+    for a, b, name in ev:
+        per.setdefault(name[:60], []).append(b - a)
+    for name, ds in sorted(per.items(), key=lambda kv: -sum(kv[1])):
+        if len(ds) >= 4 * steps and any(k in name for k in ('restrict', 'prolong', 'spmv_node', 'jacobi')):
+            ds = sorted(ds)
+            q = [ds[int(f * (len(ds) - 1))] for f in (0.1, 0.3, 0.5, 0.7, 0.9)]
+            print('   %-60s us at 10/30/50/70/90 %%: %s' % (name, ' '.join('%.1f' % v for v in q)))
     rows = []
     for e in prof.key_averages():
         t = getattr(e, 'device_time_total', None)
