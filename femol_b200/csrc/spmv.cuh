@@ -46,13 +46,27 @@ spmv_node_kernel(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, const int
             typedef typename femol_pair<VT>::type VT2;
             const VT2* __restrict__ v2 = reinterpret_cast<const VT2*>(vals) + base2;
             const int n2 = len * H;
-            for (int c = g; c < n2; c += G) {
-                const int k = c / H, h = c - k * H;
-                const int32_t j = __ldg(&adj_idx[pb + k]);
-                const VT2 a = __ldcs(&v2[c]);
-                const double2 b = __ldg(&x2[(int64_t)j * H + h]);
-                acc += (double)a.x * b.x;
-                acc += (double)a.y * b.y;
+            // four entries per lane in flight: the column index, the value and then the gathered x of all four are
+            // requested before the first product (the plain loop serialised index -> x round trips)
+            for (int c0 = g; c0 < n2; c0 += 4 * G) {
+                int32_t j[4]; VT2 a[4]; int hh[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = c0 + q * G;
+                    const bool ok = c < n2;
+                    const int k = c / H;
+                    hh[q] = c - k * H;
+                    j[q] = ok ? __ldg(&adj_idx[pb + k]) : -1;
+                    if (ok) a[q] = __ldcs(&v2[c]); else { a[q].x = 0; a[q].y = 0; }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (j[q] >= 0) {
+                        const double2 b = __ldg(&x2[(int64_t)j[q] * H + hh[q]]);
+                        acc += (double)a[q].x * b.x;
+                        acc += (double)a[q].y * b.y;
+                    }
+                }
             }
         }
 #pragma unroll
