@@ -322,10 +322,6 @@ prolong_add_kernel(int64_t nxf64, int64_t nyf64, int64_t nxc64, const uint8_t* _
     }
 }
 
-__global__ void __launch_bounds__(256) to_float_kernel(int64_t n, const double* __restrict__ a, float* __restrict__ b) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) b[i] = (float)a[i];
-}
-
 // ---- smoother ------------------------------------------------------------------------------------------------------
 // FIRST: e = omega Dinv r ; else e += omega Dinv (r - Ke)
 template <int ND, bool FIRST>
@@ -371,46 +367,43 @@ __global__ void csr_to_dense(int64_t n, const int32_t* __restrict__ adj_ptr, con
 // In-place Gauss-Jordan inversion of the SPD matrix A (n x n) without pivoting; a non-positive pivot (a coarse
 // dof that lost all its stiffness) is replaced by an identity row/column.
 __global__ void __launch_bounds__(1024)
-dense_inverse(int n, double* __restrict__ A) {
-    __shared__ double s_piv;
+dense_inverse(int n, double* __restrict__ Ag) {
+    extern __shared__ double A[];   // the whole matrix (n <= GMG_COARSE_MAX_DOF): ~4 n barriers, no global round trips
     __shared__ double s_scale;
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) A[t] = Ag[t];
+    __syncthreads();
     if (threadIdx.x == 0) {
         double mx = 0.0;
-        for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(A[(int64_t)i * n + i]));
+        for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(A[i * n + i]));
         s_scale = mx;
     }
     __syncthreads();
     const double tiny = 1e-13 * s_scale;
     for (int k = 0; k < n; ++k) {
-        if (threadIdx.x == 0) s_piv = A[(int64_t)k * n + k];
-        __syncthreads();
-        double piv = s_piv;
+        const double piv = A[k * n + k];
+        __syncthreads();              // everybody has read the pivot before row k is rewritten
         const bool dead = !(piv > tiny);
         if (dead) {  // decouple dof k
-            for (int j = threadIdx.x; j < n; j += blockDim.x) { A[(int64_t)k * n + j] = 0.0; A[(int64_t)j * n + k] = 0.0; }
-            __syncthreads();
-            if (threadIdx.x == 0) A[(int64_t)k * n + k] = 0.0;
+            for (int j = threadIdx.x; j < n; j += blockDim.x) { A[k * n + j] = 0.0; A[j * n + k] = 0.0; }
             __syncthreads();
             continue;
         }
         const double ip = 1.0 / piv;
         // row k scaled (pivot element becomes 1/piv)
-        for (int j = threadIdx.x; j < n; j += blockDim.x) {
-            const int64_t o = (int64_t)k * n + j;
-            A[o] = (j == k) ? ip : A[o] * ip;
-        }
+        for (int j = threadIdx.x; j < n; j += blockDim.x) A[k * n + j] = (j == k) ? ip : A[k * n + j] * ip;
         __syncthreads();
         // eliminate column k from every other row
-        for (int64_t t = threadIdx.x; t < (int64_t)n * n; t += blockDim.x) {
-            const int i = (int)(t / n), j = (int)(t - (int64_t)i * n);
+        for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+            const int i = t / n, j = t - i * n;
             if (i == k || j == k) continue;
-            A[t] -= A[(int64_t)i * n + k] * A[(int64_t)k * n + j];
+            A[t] -= A[i * n + k] * A[k * n + j];
         }
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += blockDim.x)
-            if (i != k) A[(int64_t)i * n + k] = -A[(int64_t)i * n + k] * ip;
+            if (i != k) A[i * n + k] = -A[i * n + k] * ip;
         __syncthreads();
     }
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) Ag[t] = A[t];
 }
 
 __global__ void __launch_bounds__(256)
@@ -1112,8 +1105,8 @@ extern "C" int femol_gmg_setup(femol_gmg* g, const double* e_base, const double*
         int rc = femol_assemble(C.plan, C.ke, 1, nullptr, 0, nullptr, 1.0, C.fixed, nullptr, C.vals, st);
         if (rc != FEMOL_OK) return rc;
         if (C.vals32) {
-            to_float_kernel<<<grid_for(C.plan->nnz), 256, 0, st>>>(C.plan->nnz, C.vals, C.vals32);
-            FEMOL_LAUNCH_CHECK();
+            rc = femol_to_f32_launch(C.plan, C.vals, C.vals32, st);
+            if (rc != FEMOL_OK) return rc;
         }
     }
     for (int l = 0; l < g->n_levels - 1; ++l) {
@@ -1124,7 +1117,15 @@ extern "C" int femol_gmg_setup(femol_gmg* g, const double* e_base, const double*
     FEMOL_CUDA_CHECK(cudaMemsetAsync(g->coarse_inv, 0, CL.n * CL.n * sizeof(double), st));
     csr_to_dense<<<grid_for(CL.n), 256, 0, st>>>(CL.n, CL.plan->adj_ptr, CL.plan->adj_idx, nd, CL.vals, g->coarse_inv);
     FEMOL_LAUNCH_CHECK();
-    dense_inverse<<<1, 1024, 0, st>>>((int)CL.n, g->coarse_inv);
+    {
+        static bool configured = false;
+        if (!configured) {
+            FEMOL_CUDA_CHECK(cudaFuncSetAttribute(dense_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  GMG_COARSE_MAX_DOF * GMG_COARSE_MAX_DOF * (int)sizeof(double)));
+            configured = true;
+        }
+    }
+    dense_inverse<<<1, 1024, CL.n * CL.n * sizeof(double), st>>>((int)CL.n, g->coarse_inv);
     FEMOL_LAUNCH_CHECK();
     return FEMOL_OK;
 }

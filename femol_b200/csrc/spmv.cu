@@ -60,16 +60,120 @@ int femol_spmv_launch(femol_plan_t p, const double* vals, const double* x, doubl
     return rc;
 }
 
+// ---- single-precision copies of assembled operators (mixed-precision multigrid levels) ---------------------------
+// ndof = 2: NODE-BLOCKED layout, one float4 (a00 a01 a10 a11) per node pair in adjacency order, so a lane fetches a
+// whole 2 x 2 block with one 16-byte request and uses the gathered x for both rows (the row-major float2 stream
+// needed twice the requests per byte and ran at 3.2 TB/s).  ndof = 6: CSR order, converted element-wise.
+namespace {
+
+__global__ void __launch_bounds__(256)
+to_f32_blocked2(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, const double* __restrict__ vals, float4* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+        const int pb = adj_ptr[i], len = adj_ptr[i + 1] - pb;
+        const double* r0 = vals + 4 * (int64_t)pb;
+        const double* r1 = r0 + 2 * len;
+        for (int k = 0; k < len; ++k)
+            out[pb + k] = make_float4((float)r0[2 * k], (float)r0[2 * k + 1], (float)r1[2 * k], (float)r1[2 * k + 1]);
+    }
+}
+
+__global__ void __launch_bounds__(256) to_f32_plain(int64_t n, const double* __restrict__ a, float* __restrict__ b) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) b[i] = (float)a[i];
+}
+
+// G lanes per NODE (ndof = 2); MODE as in spmv_node_kernel
+template <int G, int MODE>
+__global__ void __launch_bounds__(256)
+spmv_block2_f32_kernel(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx,
+                       const float4* __restrict__ blk, const double* __restrict__ x, double* __restrict__ y,
+                       const double* __restrict__ rhs, const double* __restrict__ dinv, double omega) {
+    const int g = threadIdx.x % G;
+    const int64_t node0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x / G;
+    const int64_t n_iter = (n_nodes + stride - 1) / stride;
+    const double2* __restrict__ x2 = reinterpret_cast<const double2*>(x);
+    for (int64_t it = 0; it < n_iter; ++it) {
+        const int64_t i = node0 + it * stride;
+        double a0 = 0.0, a1 = 0.0;
+        if (i < n_nodes) {
+            const int pb = __ldg(&adj_ptr[i]);
+            const int len = __ldg(&adj_ptr[i + 1]) - pb;
+            for (int k0 = g; k0 < len; k0 += 4 * G) {
+                int32_t j[4]; float4 a[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k = k0 + q * G;
+                    const bool ok = k < len;
+                    j[q] = ok ? __ldg(&adj_idx[pb + k]) : -1;
+                    a[q] = ok ? __ldcs(&blk[pb + k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (j[q] >= 0) {
+                        const double2 b = __ldg(&x2[j[q]]);
+                        a0 += (double)a[q].x * b.x; a0 += (double)a[q].y * b.y;
+                        a1 += (double)a[q].z * b.x; a1 += (double)a[q].w * b.y;
+                    }
+            }
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        }
+        if (g == 0 && i < n_nodes) {
+            double2 out = make_double2(a0, a1);
+            if (MODE >= 1) {
+                const double2 r = __ldg(reinterpret_cast<const double2*>(rhs) + i);
+                out.x = r.x - a0; out.y = r.y - a1;
+            }
+            if (MODE == 2) {
+                const double2 d0 = __ldg(reinterpret_cast<const double2*>(dinv) + 2 * i);
+                const double2 d1 = __ldg(reinterpret_cast<const double2*>(dinv) + 2 * i + 1);
+                const double2 xi = __ldg(&x2[i]);
+                out = make_double2(xi.x + omega * (d0.x * out.x + d0.y * out.y), xi.y + omega * (d1.x * out.x + d1.y * out.y));
+            }
+            reinterpret_cast<double2*>(y)[i] = out;
+        }
+    }
+}
+
+template <int MODE>
+int launch_block2(femol_plan_t p, const float* vals32, const double* x, double* y, const femol_epilogue& ep, cudaStream_t st) {
+    constexpr int G = 4;
+    int64_t blocks = (p->n_nodes * G + 255) / 256;
+    const int64_t cap = (int64_t)p->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    spmv_block2_f32_kernel<G, MODE><<<(int)blocks, 256, 0, st>>>(p->n_nodes, p->adj_ptr, p->adj_idx,
+                                                                 reinterpret_cast<const float4*>(vals32), x, y, ep.rhs, ep.dinv, ep.omega);
+    FEMOL_LAUNCH_CHECK();
+    return FEMOL_OK;
+}
+
+}  // namespace
+
+int femol_to_f32_launch(femol_plan_t p, const double* vals, float* vals32, cudaStream_t st) {
+    if (p->ndof == 2) {
+        const int grid = femol_grid_for(p->n_nodes, 256, p->sm_count, 8);
+        to_f32_blocked2<<<grid, 256, 0, st>>>(p->n_nodes, p->adj_ptr, vals, reinterpret_cast<float4*>(vals32));
+    } else {
+        const int grid = femol_grid_for(p->nnz, 256, p->sm_count, 8);
+        to_f32_plain<<<grid, 256, 0, st>>>(p->nnz, vals, vals32);
+    }
+    FEMOL_LAUNCH_CHECK();
+    return FEMOL_OK;
+}
+
 int femol_spmv_f32_epilogue_launch(femol_plan_t p, const float* vals32, const double* x, double* y, const femol_epilogue& ep,
                                    cudaStream_t st) {
-    if (ep.mode == FEMOL_EPI_RESIDUAL) {
-        if (p->ndof == 2) return spmv_node_launch<2, 1, float>(p, vals32, x, y, nullptr, nullptr, nullptr, st, ep.rhs);
-        if (p->ndof == 6) return spmv_node_launch<6, 1, float>(p, vals32, x, y, nullptr, nullptr, nullptr, st, ep.rhs);
-    } else if (ep.mode == FEMOL_EPI_JACOBI && p->ndof == 2) {
-        return spmv_node_launch<2, 2, float>(p, vals32, x, y, nullptr, ep.dot_out, ep.red_ws, st, ep.rhs, ep.dinv, ep.omega);
-    } else if (ep.mode == FEMOL_EPI_NONE) {
-        if (p->ndof == 2) return spmv_node_launch<2, 0, float>(p, vals32, x, y, nullptr, nullptr, nullptr, st);
-        if (p->ndof == 6) return spmv_node_launch<6, 0, float>(p, vals32, x, y, nullptr, nullptr, nullptr, st);
+    if (p->ndof == 2 && !ep.dot_out) {
+        if (ep.mode == FEMOL_EPI_NONE) return launch_block2<0>(p, vals32, x, y, ep, st);
+        if (ep.mode == FEMOL_EPI_RESIDUAL) return launch_block2<1>(p, vals32, x, y, ep, st);
+        if (ep.mode == FEMOL_EPI_JACOBI) return launch_block2<2>(p, vals32, x, y, ep, st);
+    } else if (p->ndof == 6) {
+        if (ep.mode == FEMOL_EPI_RESIDUAL) return spmv_node_launch<6, 1, float>(p, vals32, x, y, nullptr, nullptr, nullptr, st, ep.rhs);
+        if (ep.mode == FEMOL_EPI_NONE) return spmv_node_launch<6, 0, float>(p, vals32, x, y, nullptr, nullptr, nullptr, st);
     }
     femol_set_error("femol_spmv_f32: mode %d not available for ndof %d", ep.mode, p->ndof);
     return FEMOL_E_ARG;

@@ -155,6 +155,8 @@ struct femol_epilogue {
 bool femol_apply_has_jacobi(femol_plan_t p, const double* vals);
 int femol_apply_epilogue_launch(femol_plan_t p, const double* vals, const double* x, double* y, const femol_epilogue& ep,
                                 cudaStream_t st);
-// CSR product from single-precision values (mixed-precision multigrid levels): modes 1 and, for ndof = 2, 2
+// single-precision copy of an assembled operator (ndof = 2: node-blocked float4 layout, ndof = 6: CSR order) and the
+// product from it (mixed-precision multigrid levels): modes 0-2 for ndof = 2, modes 0-1 for ndof = 6
+int femol_to_f32_launch(femol_plan_t p, const double* vals, float* vals32, cudaStream_t st);
 int femol_spmv_f32_epilogue_launch(femol_plan_t p, const float* vals32, const double* x, double* y, const femol_epilogue& ep,
                                    cudaStream_t st);
