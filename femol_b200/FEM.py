@@ -139,6 +139,7 @@ class FEM_Problem(object):
         self.modal_max_iter = 500
         self.modal_inner_iters = 200     # block-CG iterations on K per LOBPCG preconditioner application
         self.modal_inner_tol = 1e-3
+        self.modal_gmg_iters = 8         # structured grids: multigrid-CG iterations per column instead of the block-CG
         # Reissner-Mindlin drilling rotations: K_tz is the diagonal set to 1 per element (elements.py:1071)
         # and the consistent mass couples tz only with tz, so the pencil has one exactly decoupled pure-tz
         # mode per free node (a dense cluster of spurious low frequencies).  They are projected out of the
@@ -508,8 +509,12 @@ class FEM_Problem(object):
             bits = (mask.to(torch.int32)[:, None] >> torch.arange(self.N_dof, device=d.dev, dtype=torch.int32)[None]) & 1
             X0[bits.reshape(-1).bool()] = 0.0
         inner = self.preconditioner if self.preconditioner in ('none', 'jacobi', 'block_jacobi') else 'block_jacobi'
+        # structured grids: T ~ K^-1 by a few multigrid-preconditioned CG iterations per column; otherwise by
+        # `modal_inner_iters` block-CG iterations with the (block-)diagonal inverse
+        gmg = self._gmg_ready() if (self.preconditioner in ('auto', 'gmg') and self._effective_preconditioner() == 'gmg') else None
         ops = _lobpcg.DeviceOps(d.plan, self._Kv, self._Mv, mask, m, _PRECOND[inner], X0,
-                                inner_iters=self.modal_inner_iters, inner_tol=self.modal_inner_tol)
+                                inner_iters=self.modal_inner_iters, inner_tol=self.modal_inner_tol, gmg=gmg,
+                                gmg_iters=self.modal_gmg_iters)
         lam, rel, its = _lobpcg.lobpcg(ops, m, k, tol=self.modal_tol, max_iter=self.modal_max_iter)
         V = ops.vectors()
         self._X_modal = V.clone()

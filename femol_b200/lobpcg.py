@@ -40,7 +40,7 @@ def _rayleigh_ritz(A, B, m):
     return w[:m], (T @ c[:, :m]) * d[:, None]
 
 
-def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False, stall_window=2):
+def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False, stall_window=5):
     """Run LOBPCG on `ops` (which already holds the initial block in S[:, :m]).
 
     Returns (lambda[m], rel_resid[m], iterations).  On exit ops.S[:, :m] holds M-orthonormal Ritz vectors,
@@ -58,7 +58,7 @@ def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False, stall_window=2):
     rel = np.full(m, np.inf)
     it = 0
     lam_prev = lam.copy()
-    history, calm = [], 0
+    best, since_best = np.inf, 0
     for it in range(1, max_iter + 1):
         ops.residual(lam)                                       # R -> W slot
         rn = np.sqrt(np.diag(ops.gram('S', 'S', m, m, m, m)))
@@ -70,18 +70,17 @@ def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False, stall_window=2):
             it -= 1
             break
         # Attainable accuracy: ||K v - l M v|| / ||K v|| cannot drop below ~eps * cond.  Once the Ritz values
-        # have stopped moving (1e-11 relative) AND the worst residual is no longer halving over two iterations,
-        # `stall_window` iterations in a row, further iterations only add noise (the residuals drift up again).
+        # have stopped moving (1e-11 relative) AND the worst residual has set no new minimum (by 2 %) for
+        # `stall_window` iterations, further iterations only add noise (the residuals drift up again).  Slow but
+        # steady convergence keeps setting new minima and is not stopped.
         worst = float(np.max(rel[:k]))
-        history.append(worst)
-        slow = len(history) >= 3 and worst >= 0.5 * history[-3]
-        if slow and np.all(np.abs(lam[:k] - lam_prev[:k]) <= 1e-11 * np.abs(lam[:k])):
-            calm += 1
-            if calm >= stall_window:
-                it -= 1
-                break
+        if worst < 0.98 * best:
+            best, since_best = worst, 0
         else:
-            calm = 0
+            since_best += 1
+        if since_best >= stall_window and np.all(np.abs(lam[:k] - lam_prev[:k]) <= 1e-11 * np.abs(lam[:k])):
+            it -= 1
+            break
         lam_prev = lam.copy()
         ops.precondition()                                      # W <- T R  (fixed dofs zeroed)
         # M-orthogonalise W against X, then M-orthonormalise W (Cholesky)
@@ -124,16 +123,22 @@ def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False, stall_window=2):
 class DeviceOps(object):
     """CUDA implementation of the block operations (csrc/lobpcg.cu through the C-ABI)."""
 
-    def __init__(self, plan, k_vals, m_vals, fixed_mask, m, precond_kind, X0, inner_iters=0, inner_tol=1e-2):
+    def __init__(self, plan, k_vals, m_vals, fixed_mask, m, precond_kind, X0, inner_iters=0, inner_tol=1e-2, gmg=None,
+                 gmg_iters=8):
         """precond_kind: diagonal / block-diagonal inverse used directly (inner_iters = 0) or as the inner
-        preconditioner of `inner_iters` block-CG iterations on K (T ~ K^-1, femol_block_pcg)."""
+        preconditioner of `inner_iters` block-CG iterations on K (T ~ K^-1, femol_block_pcg).
+        gmg: multigrid hierarchy of K (femol_gmg handle, structured grids): T ~ K^-1 by at most `gmg_iters`
+        multigrid-preconditioned CG iterations per column (femol_pcg_gmg) instead of the block-CG."""
         import torch
         from . import _lib
         self._lib, self._torch = _lib, torch
         self.plan, self.k_vals, self.m_vals, self.fixed = plan, k_vals, m_vals, fixed_mask
         self.m = m
         self.inner_iters, self.inner_tol = int(inner_iters), float(inner_tol)
+        self.gmg, self.gmg_iters = gmg, int(gmg_iters)
         self._bp_ws = None
+        self._gmg_ws = None
+        self._keep = None
         n = X0.shape[0]
         self.n = n
         dev = X0.device
@@ -209,9 +214,35 @@ class DeviceOps(object):
         L.call('femol_block_residual', self.n, self.m, self._p('KS', 0), 3 * self.m, self._p('MS', 0), 3 * self.m,
                L.ptr(self.lam_dev), self._p('S', self.m), 3 * self.m, L.stream())
 
+    def _precondition_gmg(self):
+        """W <- P K^-1 W column by column (P: zero the masked dofs), K^-1 by a few multigrid-preconditioned CG
+        iterations (a variable preconditioner, which LOBPCG tolerates)."""
+        import ctypes
+        L, torch = self._lib, self._torch
+        m = self.m
+        S = self.buf[self.cur]['S']
+        if self._gmg_ws is None:
+            nd = int(L.load().femol_pcg_gmg_workspace_doubles(self.plan))
+            self._gmg_ws = torch.empty(nd, dtype=torch.float64, device=S.device)
+            if self.fixed is not None:
+                ndof = self.n // self._n_nodes()
+                bits = (self.fixed.to(torch.int32)[:, None] >> torch.arange(ndof, device=S.device, dtype=torch.int32)[None]) & 1
+                self._keep = (1 - bits).reshape(-1).to(torch.float64)
+        it, rr = ctypes.c_int(0), ctypes.c_double(0.0)
+        for c in range(m, 2 * m):
+            r = S[:, c].contiguous()
+            z = torch.zeros_like(r)
+            L.call('femol_pcg_gmg', self.plan, self.gmg, L.ptr(self.k_vals), L.ptr(r), L.ptr(z), self.inner_tol,
+                   self.gmg_iters, L.ptr(self._gmg_ws), ctypes.byref(it), ctypes.byref(rr), L.stream())
+            if self._keep is not None:
+                z.mul_(self._keep)
+            S[:, c] = z
+
     def precondition(self):
         L = self._lib
         fixed = L.ptr(self.fixed) if self.fixed is not None else None
+        if self.gmg is not None:
+            return self._precondition_gmg()
         if self.inner_iters > 0:
             if self._bp_ws is None:
                 nd = int(L.load().femol_block_pcg_workspace_doubles(self.plan, self.m))
