@@ -333,6 +333,17 @@ def run_gpu(args):
                         'frac_on_kernel_bytes': asm_kernel / t_asm / 1e9 / peak,
                         'launches_in_timed_region': args.steps,
                         'share_of_step': args.steps * t_asm / dt if dt > 0 else None}
+        # stress recovery: N_e (16 conn + 8 x + 32 out) + 16 n (xy) + 8 n (U) algorithmic bytes
+        Tb = torch.from_numpy(np.ascontiguousarray(problem.tensors[0], dtype=np.float64)).cuda()
+        s_out = torch.empty((4, n_elem), dtype=torch.float64, device='cuda')
+        t_str = time_kernel(torch, lambda: L.femol_stress_q4(d.plan, d.xy.data_ptr(), xv.data_ptr(), Tb.data_ptr(), None,
+                                                             opt.x_device.data_ptr(), s_out.data_ptr(), st), 20)
+        stress_bytes = n_elem * 56 + 24 * d.n_nodes
+        roofline_stress = {'kernel': 'stress_q4_kernel (Mesh.stress_from_displacement)', 'bound': 'hbm',
+                           'achieved': stress_bytes / t_str / 1e9, 'peak': peak, 'unit': 'GB/s',
+                           'frac': stress_bytes / t_str / 1e9 / peak, 'traffic': None,
+                           'algorithmic_bytes_per_launch': stress_bytes, 'avg_launch_s': t_str,
+                           'launches_in_timed_region': 0}
         cpu = None
         if not args.no_cpu_baseline:
             cdt, cval = cpu_sample(args.sample_nx, args.sample_ny, args.nx * args.ny, steps=1, warmup=0)
@@ -352,7 +363,7 @@ def run_gpu(args):
                 'e2e': {'value': world * args.steps / dt_e2e, 'unit': UNIT, 'h2d_bytes_per_step': 8 * n_elem,
                         'd2h_bytes_per_step': 8 * n_elem + 64, 'pcg_iterations_per_step': e2e_iters},
                 'gpu_launches': launches, 'roofline': roofline, 'roofline_spmv_csr': spmv_csr,
-                'roofline_assembly': roofline_asm,
+                'roofline_assembly': roofline_asm, 'roofline_stress': roofline_stress,
                 'cpu_baseline': cpu, 'clocks': clocks,
                 'trajectory': {'change': [l[0] for l in log], 'compliance': [l[1] for l in log],
                                'pcg_relres': [l[2] for l in log]}}

@@ -234,6 +234,7 @@ class FEM_Problem(object):
     def device(self):
         if self._dev is None:
             self._dev = _Device(self.mesh, self.N_dof)
+            self.mesh._femol_device = self._dev      # Mesh.stress_from_displacement reuses the plan
         return self._dev
 
     def _bc_key(self):

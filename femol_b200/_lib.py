@@ -37,6 +37,7 @@ SIGNATURES = {
     'femol_spmv': (c_int, [P, P, P, P, P]),
     'femol_spmv_csr': (c_int, [c_i64, P, P, P, P, P, P]),
     'femol_plan_set_matrix_free': (c_int, [P, c_i64, c_i64, P, P, P, P, P]),
+    'femol_stress_q4': (c_int, [P, P, P, P, P, P, P, P]),
     'femol_apply': (c_int, [P, P, P, P, P]),
     'femol_apply_epilogue': (c_int, [P, P, P, P, c_int, P, P, c_dbl, P]),
     'femol_pcg_workspace_doubles': (c_i64, [P]),

@@ -392,6 +392,56 @@ dot_kernel(int64_t n, const double* __restrict__ a, const double* __restrict__ b
     grid_sum_finish<1>(s, red_ws, red_ticket(red_ws), out, smem);
 }
 
+
+// ---- centroid stresses of Q4 plane-stress elements (Mesh.stress_from_displacement, mesh.py:387-425) ---------------
+// One thread per element: gather the 4 nodes, B(0,0) from the Jacobian at the centroid, S = T B u with
+// T = T_base, T_base x^3 or T_base + T_coat x^3 (exponent hard-coded in the reference), and the reference's
+// "von Mises" combination.  Structure-of-arrays output [4][n_elem] = Sx | Sy | Sxy | Sv.
+__global__ void __launch_bounds__(256)
+stress_q4_kernel(int64_t n_elem, const int32_t* __restrict__ conn, const double* __restrict__ xy,
+                 const double* __restrict__ u, int ndof, const double* __restrict__ t_base,
+                 const double* __restrict__ t_coat, const double* __restrict__ x, double* __restrict__ out) {
+    __shared__ double s_t[18];
+    if (threadIdx.x < 9) { s_t[threadIdx.x] = t_base[threadIdx.x]; s_t[9 + threadIdx.x] = t_coat ? t_coat[threadIdx.x] : 0.0; }
+    __syncthreads();
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_elem; e += (int64_t)gridDim.x * blockDim.x) {
+        const int4 c = __ldg(reinterpret_cast<const int4*>(conn) + e);
+        const int nodes[4] = {c.x, c.y, c.z, c.w};
+        double X[4], Y[4], ux[4], uy[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const double2 p = __ldg(reinterpret_cast<const double2*>(xy) + nodes[a]);
+            X[a] = p.x; Y[a] = p.y;
+            const double2 d = __ldg(reinterpret_cast<const double2*>(u + (int64_t)nodes[a] * ndof));
+            ux[a] = d.x; uy[a] = d.y;
+        }
+        // dN/dxi = (-1, 1, 1, -1)/4, dN/deta = (-1, -1, 1, 1)/4 at the centroid
+        const double j00 = 0.25 * (-X[0] + X[1] + X[2] - X[3]), j01 = 0.25 * (-Y[0] + Y[1] + Y[2] - Y[3]);
+        const double j10 = 0.25 * (-X[0] - X[1] + X[2] + X[3]), j11 = 0.25 * (-Y[0] - Y[1] + Y[2] + Y[3]);
+        const double idet = 1.0 / (j00 * j11 - j01 * j10);
+        const double dxi[4] = {-0.25, 0.25, 0.25, -0.25}, det[4] = {-0.25, -0.25, 0.25, 0.25};
+        double exx = 0.0, eyy = 0.0, gxy = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const double dx = idet * (j11 * dxi[a] - j01 * det[a]);
+            const double dy = idet * (-j10 * dxi[a] + j00 * det[a]);
+            exx += dx * ux[a]; eyy += dy * uy[a]; gxy += dy * ux[a] + dx * uy[a];
+        }
+        double w = 1.0;
+        if (x) { const double xe = __ldg(&x[e]); w = xe * xe * xe; }
+        double S[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double sb = s_t[3 * r] * exx + s_t[3 * r + 1] * eyy + s_t[3 * r + 2] * gxy;
+            const double sc = s_t[9 + 3 * r] * exx + s_t[9 + 3 * r + 1] * eyy + s_t[9 + 3 * r + 2] * gxy;
+            S[r] = t_coat ? sb + w * sc : w * sb;
+        }
+        const double a0 = S[0] - S[1], a1 = S[1] - S[2], a2 = S[2] - S[0];
+        out[e] = S[0]; out[n_elem + e] = S[1]; out[2 * n_elem + e] = S[2];
+        out[3 * n_elem + e] = sqrt(0.5 * (a0 * a0 + a1 * a1 + a2 * a2));
+    }
+}
+
 }  // namespace
 
 extern "C" int femol_sens_compliance(femol_plan_t p, const double* e_base, int base_pe, const double* e_coat, int coat_pe,
@@ -469,6 +519,17 @@ extern "C" int femol_dot(int64_t n, const double* a, const double* b, double* ou
     FEMOL_REQUIRE(a && b && out && ws && n > 0, "femol_dot: bad argument");
     const int grid = femol_grid_for(n, 256, femol_sm_count(), 4);
     dot_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, a, b, out, ws);
+    FEMOL_LAUNCH_CHECK();
+    return FEMOL_OK;
+}
+
+extern "C" int femol_stress_q4(femol_plan_t p, const double* xy, const double* u, const double* t_base, const double* t_coat,
+                               const double* x, double* out, void* stream) {
+    FEMOL_REQUIRE(p && xy && u && t_base && out, "femol_stress_q4: null argument");
+    FEMOL_REQUIRE(p->nn == 4 && p->ndof >= 2 && p->ndof % 2 == 0, "femol_stress_q4: 4-node elements with an even number of dofs per node only");
+    if (p->n_elem == 0) return FEMOL_OK;
+    const int grid = femol_grid_for(p->n_elem, 256, p->sm_count, 8);
+    stress_q4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->n_elem, p->conn, xy, u, p->ndof, t_base, t_coat, x, out);
     FEMOL_LAUNCH_CHECK();
     return FEMOL_OK;
 }

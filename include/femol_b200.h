@@ -243,6 +243,14 @@ int femol_oc_update(int64_t n_elem, const double* x, double* dc, int mode, doubl
                     const double* areas, const uint8_t* mask, double* x_new, double* scalars_out,
                     double* ws, void* stream);
 
+/* Centroid stresses of Q4 plane-stress elements.  Replaces Mesh.stress_from_displacement + Q4.stress
+ * (mesh.py:387-425, elements.py:1144-1152): S = T B(0,0) u_e with T = t_base (x NULL), t_base * x^3 (t_coat NULL) or
+ * t_base + t_coat * x^3 (the exponent 3 is the reference's), and Sv = sqrt(((Sx-Sy)^2 + (Sy-Sxy)^2 + (Sxy-Sx)^2) / 2)
+ * exactly as the reference combines them.  xy [n_nodes][2], u [n_nodes][ndof] (Ux, Uy first), t_* [3][3] device,
+ * out [4][n_elem] = Sx | Sy | Sxy | Sv. */
+int femol_stress_q4(femol_plan_t plan, const double* xy, const double* u, const double* t_base, const double* t_coat,
+                    const double* x, double* out, void* stream);
+
 /* ---- K11: modal assurance criterion (utils.py:436-447; TOM.py:383-386) ----------------------
  * mac_out[i] = (V_i . v_ref)^2 / ((V_i . V_i)(v_ref . v_ref)), V: [k][n] row-major; device output [k]. */
 int femol_mac(int64_t n, int k, const double* V, const double* v_ref, double* mac_out, double* ws,

@@ -662,6 +662,35 @@ def modal_solve_sparse(K, M, k=10, sigma=0.0):
     return np.sqrt(w[keep]) / (2 * np.pi), v[keep]
 
 
+def q4_stress(points, cells, U, T_base, x=None, T_coat=None):
+    """Centroid stresses of Q4 plane-stress elements (mesh.py:387-425 + elements.py:1144-1152).
+
+    S = T @ B(0, 0) @ u_e with T = T_base (no densities), T_base * x^3 (one tensor) or T_base + T_coat * x^3
+    (two tensors): the exponent 3 is hard-coded in the reference (mesh.py:412-414).  Returns Sx, Sy, Sxy and the
+    reference's "von Mises" value sqrt(((Sx-Sy)^2 + (Sy-Sxy)^2 + (Sxy-Sx)^2) / 2) (mesh.py:420), which treats
+    Sxy like a normal stress - reproduced as is."""
+    P = np.asarray(points)[:, :2]
+    S = np.zeros((len(cells), 3))
+    dxi = 0.25 * np.array([-1.0, 1.0, 1.0, -1.0])      # dN/dxi, dN/deta at the centroid
+    det = 0.25 * np.array([-1.0, -1.0, 1.0, 1.0])
+    for e, cell in enumerate(cells):
+        X, Y = P[cell, 0], P[cell, 1]
+        J = np.array([[dxi @ X, dxi @ Y], [det @ X, det @ Y]])
+        d = np.linalg.solve(J, np.stack([dxi, det]))   # rows: dN/dx, dN/dy
+        B = np.zeros((3, 8))
+        B[0, 0::2] = d[0]; B[1, 1::2] = d[1]; B[2, 0::2] = d[1]; B[2, 1::2] = d[0]
+        u = np.empty(8); u[0::2] = U[2 * cell]; u[1::2] = U[2 * cell + 1]
+        if x is None:
+            T = T_base
+        elif T_coat is None:
+            T = T_base * x[e] ** 3
+        else:
+            T = T_base + T_coat * x[e] ** 3
+        S[e] = T @ B @ u
+    Sv = np.sqrt(((S[:, 0] - S[:, 1]) ** 2 + (S[:, 1] - S[:, 2]) ** 2 + (S[:, 2] - S[:, 0]) ** 2) / 2)
+    return S[:, 0], S[:, 1], S[:, 2], Sv
+
+
 def mac(v1, v2):
     """utils.py:436-447"""
     return abs(v1 @ v2) ** 2 / ((v1 @ v1) * (v2 @ v2))

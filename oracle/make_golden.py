@@ -188,11 +188,36 @@ def gen_case(name):
     return out
 
 
+def gen_stress():
+    """Mesh.stress_from_displacement (mesh.py:387-425) of the reference on a jittered Q4 plane-stress mesh: no
+    densities, one tensor with densities, base + coating tensors with densities."""
+    case = cases.CASES['comp_q4_jitter_coat_8x4']
+    problem = cases.build_problem(FEMOL, case)
+    mesh = quiet(problem.solve, verbose=False)
+    U = mesh.U.copy()
+    Tb, Tc = problem.tensors[0], problem.coat_tensors[0]
+    out = {'points': mesh.points.copy(), 'cells': np.asarray(mesh.cells['quad']), 'U': U, 'T_base': Tb, 'T_coat': Tc}
+    x = cases.density_field(mesh.N_ele, seed=7)
+    variants = {'plain': ((Tb,), None), 'one': ((Tb,), x), 'two': ((Tb, Tc), x)}
+    for key, (tensors, dens) in variants.items():
+        mesh.cell_data.pop('X', None)
+        if dens is not None:
+            mesh.cell_data['X'] = {'quad': dens}
+        mesh.stress_from_displacement(*tensors)
+        for comp in ('Sx', 'Sy', 'Sxy', 'Sv'):
+            out['%s_%s' % (key, comp)] = np.asarray(mesh.cell_data[comp]['quad']).copy()
+    out['x'] = x
+    np.savez_compressed(os.path.join(GOLD, 'stress_q4.npz'), **out)
+    return out
+
+
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
-    todo = sys.argv[1:] or (['elements'] + list(cases.CASES))
+    todo = sys.argv[1:] or (['elements', 'stress'] + list(cases.CASES))
     for name in todo:
-        if name == 'elements':
+        if name == 'stress':
+            gen_stress()
+        elif name == 'elements':
             gen_elements()
         else:
             gen_case(name)

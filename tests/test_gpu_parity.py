@@ -738,3 +738,34 @@ def test_product_epilogues(F, nx, ny, model, matrix_free):
     assert rel(y.cpu().numpy(), ref) < 1e-13
     with pytest.raises(F._lib.FemolError):
         F._lib.call('femol_apply_epilogue', d.plan, p.K_values.data_ptr(), xd.data_ptr(), xd.data_ptr(), 0, None, None, 0.0, F._lib.stream())
+
+
+def test_stress_recovery(F, golden):
+    """Mesh.stress_from_displacement (mesh.py:387-425) against the reference's own output on a jittered Q4 mesh:
+    plain tensor, tensor * X^3, base + coating * X^3; plus the call pattern after a solve and the oracle on a
+    larger random field."""
+    import torch
+    g = golden('stress_q4')
+    mesh = F.Mesh(g['points'], {'quad': g['cells']})
+    mesh.add_displacement(g['U'], 2)
+    for key, tensors, x in (('plain', (g['T_base'],), None), ('one', (g['T_base'],), g['x']),
+                            ('two', (g['T_base'], g['T_coat']), g['x'])):
+        mesh.cell_data.pop('X', None)
+        if x is not None:
+            mesh.cell_data['X'] = {'quad': x}
+        mesh.stress_from_displacement(*tensors)
+        for comp in ('Sx', 'Sy', 'Sxy', 'Sv'):
+            assert rel(mesh.cell_data[comp]['quad'], g['%s_%s' % (key, comp)]) < 1e-12, (key, comp)
+    # after a solve of the mirror API (plate problem: 6 dofs per node, Ux / Uy are the first two)
+    problem = cases.build_problem(F, cases.CASES['plate_q4_jitter_6x5'])
+    m2 = problem.solve(verbose=False)
+    m2.stress_from_displacement(problem.tensors[0])
+    ref = o.q4_stress(m2.points, np.asarray(m2.cells['quad']), np.stack([m2.point_data['Ux'], m2.point_data['Uy']], 1).reshape(-1),
+                      problem.tensors[0])
+    for comp, r in zip(('Sx', 'Sy', 'Sxy', 'Sv'), ref):
+        assert rel(m2.cell_data[comp]['quad'], r) < 1e-11 or np.abs(r).max() < 1e-300
+    # T3 / T6 meshes have no stress method in the reference
+    with pytest.raises(AttributeError):
+        m3 = F.mesh.rectangle_T3(2., 1., 2, 1)
+        m3.add_displacement(np.zeros(2 * m3.N_nodes), 2)
+        m3.stress_from_displacement(g['T_base'])
