@@ -661,7 +661,11 @@ def test_gmg_rejects_unstructured(F):
 @pytest.mark.parametrize('nx,ny,model,coating,scaled', [(32, 16, 'plane', False, True), (33, 17, 'plane', False, False),
                                                         (45, 22, 'plane', True, True), (1, 1, 'plane', False, True),
                                                         (24, 12, 'plate', False, True), (21, 13, 'plate', False, False),
-                                                        (7, 1, 'plate', False, True), (300, 211, 'plane', False, True)])
+                                                        (7, 1, 'plate', False, True), (300, 211, 'plane', False, True),
+                                                        # sizes around the 32 x 16 (plane) / 32 x 8 (plate) node tiles and the 4-tile CTA groups
+                                                        (31, 15, 'plane', False, True), (64, 33, 'plane', True, True), (65, 31, 'plane', False, False),
+                                                        (127, 5, 'plane', False, True), (31, 7, 'plate', False, True), (33, 9, 'plate', False, False),
+                                                        (95, 16, 'plate', False, True)])
 def test_matrix_free_operator_equals_assembled(F, nx, ny, model, coating, scaled):
     """femol_apply (the stencil the solvers use on structured grids, csrc/stencil.cu) against the assembled CSR
     product and scipy: same K including the Dirichlet rows / columns (FEM.py:902-930)."""
@@ -769,3 +773,32 @@ def test_stress_recovery(F, golden):
         m3 = F.mesh.rectangle_T3(2., 1., 2, 1)
         m3.add_displacement(np.zeros(2 * m3.N_nodes), 2)
         m3.stress_from_displacement(g['T_base'])
+
+
+def test_gmg_mid_size_plate_regular_levels(F):
+    """96 x 64 Mindlin plate (38 k dof): the level-1 operator (4 MB) is above the cluster-kernel threshold, so this
+    runs the regular-level path for 6 dofs per node (single-precision CSR copies, unfused post-smoothing) that the
+    small cases never reach.  The solution must satisfy the ASSEMBLED double-precision system."""
+    import torch
+    p, _ = _gmg_problem(F, 96, 64, 'plate')
+    # a smooth density field (like a filtered SIMP design): element-wise random densities with a 1e9 stiffness
+    # contrast defeat any geometric coarsening (9 866 multigrid-CG iterations against 14 241 block-Jacobi ones here)
+    i, j = np.divmod(np.arange(96 * 64), 64)
+    x = 0.55 + 0.45 * np.sin(2 * np.pi * i / 96) * np.cos(2 * np.pi * j / 64)
+    p.solver_rtol = 1e-8
+    p.assemble('K', X={'quad': x}, p=3)
+    p.preconditioner = 'gmg'
+    U = p.solve_device()
+    assert p.solver_info['converged'], p.solver_info
+    d = p.device
+    y = torch.empty_like(U)
+    F._lib.call('femol_spmv', d.plan, p.K_values.data_ptr(), U.data_ptr(), y.data_ptr(), F._lib.stream())
+    # attainable accuracy on this plate with densities down to 1e-3 (cond ~ 1e10) is a few 1e-7, with or without
+    # the single-precision level copies (FEMOL_GMG_F32=0 gives 1.7e-7)
+    assert float((y - p._F_dev).norm() / p._F_dev.norm()) < 1e-6
+    it_mg = p.solver_info['iterations']
+    p.preconditioner = 'block_jacobi'
+    p._U_dev = None
+    U_bj = p.solve_device()
+    assert it_mg < p.solver_info['iterations'] // 2, (it_mg, p.solver_info)
+    assert rel(U.cpu().numpy(), U_bj.cpu().numpy()) < 1e-4
