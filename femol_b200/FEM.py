@@ -399,7 +399,7 @@ class FEM_Problem(object):
         if self.physics == 'displacement':
             return self._displacement_solve(verbose)
         elif self.physics == 'modal':
-            return self._modal_solve(verbose)
+            return self._modal_solve(verbose, filtre)
 
     def solve_device(self):
         """K U = F on the device; returns the device displacement tensor (no host copy)."""
@@ -522,10 +522,52 @@ class FEM_Problem(object):
         self.solver_info = {'iterations': its, 'relres': rel[:k].copy(), 'block': m}
         return lam[:k], V[:, :k].t().contiguous()
 
-    def _modal_solve(self, verbose):
-        """FEM.py:216-256: returns (sqrt(lambda)/2pi [Hz], v) with v rows = M-orthonormal modes."""
+    def _modal_solve(self, verbose, filtre=0):
+        """FEM.py:216-256: returns (sqrt(lambda)/2pi [Hz], v) with v rows = M-orthonormal modes.
+
+        The eigen-filters (FEM.py:335-418) are heuristics the reference needs to clean the FULL dense spectrum
+        (lambda = 1 pairs of the fixed dofs, drilling / mesh modes).  The block eigen-solver projects those out
+        and returns the lowest `n_modes` physical pairs, so filter 0 is the natural choice; 1 and 2 are applied
+        to the returned pairs with the reference's own rules for callers that pass them."""
         lam, V = self.modal_device()
         if verbose:
             print('Solved with LOBPCG: %(iterations)d iterations' % self.solver_info)
-        w = np.sqrt(np.maximum(lam, 0.0)) / (2 * np.pi)
-        return w, V.cpu().numpy()
+        w, v = lam, V.cpu().numpy()
+        keep = ~np.isnan(w)
+        w, v = w[keep], v[keep]
+        keep = ~np.isclose(w, 0) & (w > 0)
+        w, v = w[keep], v[keep]
+        w, v = {0: lambda a, b: (a, b), 1: self._filter_eigenvalues_1, 2: self._filter_eigenvalues_2}[filtre](w, v)
+        return np.sqrt(w) / (2 * np.pi), v
+
+    # ---- eigen-filters of the reference (host post-processing of the returned pairs) --------------------
+    def _filter_eigenvalues_1(self, w, v):
+        """FEM.py:343-351 = low-range duplicates (:405-418) then mesh modes (:392-403)."""
+        f = np.sqrt(w) / (2 * np.pi)
+        distinct = np.flatnonzero(~np.isclose(f[:-1], f[1:], 10e-5))      # third positional argument = rtol
+        start = distinct[1]                                               # IndexError like the reference if < 2
+        w, v = w[start:], v[start:]
+        if self.N_dof != 6:
+            # the reference's _filter_mesh_modes returns None for plane models and fails on unpacking
+            raise TypeError('cannot unpack non-iterable NoneType object')
+        live = ~np.isclose([np.std(vi[2::6]) for vi in v], 0)
+        return w[live], v[live]
+
+    def _filter_eigenvalues_2(self, w, v):
+        """FEM.py:353-390: skip runs of frequencies within 32 Hz of the run's first one, keep a run's first
+        frequency if it is above 1.1 Hz and its vector is not too peaked (max / mean|.| < 5)."""
+        f = np.sqrt(w) / (2 * np.pi)
+        n = f.shape[0]
+        kept = []
+        i = 0
+        while i < n - 2:
+            j = 1
+            while np.isclose(f[i], f[i + j], atol=32):
+                j += 1
+                if i + j == n:
+                    break
+            if f[i] > 1.1 and np.abs(v[i].max()) / np.abs(v[i]).mean() < 5:
+                kept.append(i)
+            i += j
+        kept = np.array(kept, dtype=int)
+        return (f[kept] * 2 * np.pi) ** 2, v[kept]

@@ -211,12 +211,34 @@ def gen_stress():
     return out
 
 
+def gen_modal_filters():
+    """The eigen-filters of the reference (FEM.py:335-418) applied to synthetic spectra."""
+    rng = np.random.default_rng(11)
+    mesh = FEMOL.mesh.rectangle_Q4(2., 2., 2, 2)
+    prob = FEMOL.FEM_Problem('modal', 'plate', mesh)
+    n = 6 * mesh.N_nodes
+    out = {}
+    # spectrum with low duplicates, in-plane (zero z-std) modes, closely spaced groups, a peaked vector
+    f = np.array([0.5, 0.5, 0.5, 0.9, 3.0, 3.00001, 40.0, 41.0, 90.0, 200.0, 260.0, 400.0, 900.0])
+    w = (2 * np.pi * f) ** 2
+    v = rng.standard_normal((f.size, n))
+    v[4, 2::6] = 0.0                 # a "mesh mode": no z component
+    v[9] = 0.0; v[9, 7] = 1.0        # a peaked vector
+    out['w'], out['v'] = w, v
+    for k in (1, 2):
+        wf, vf = {1: prob._filter_eigenvalues_1, 2: prob._filter_eigenvalues_2}[k](w.copy(), v.copy())
+        out['w%d' % k], out['v%d' % k] = np.asarray(wf), np.asarray(vf)
+    np.savez_compressed(os.path.join(GOLD, 'modal_filters.npz'), **out)
+
+
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
-    todo = sys.argv[1:] or (['elements', 'stress'] + list(cases.CASES))
+    todo = sys.argv[1:] or (['elements', 'stress', 'modal_filters'] + list(cases.CASES))
     for name in todo:
         if name == 'stress':
             gen_stress()
+        elif name == 'modal_filters':
+            gen_modal_filters()
         elif name == 'elements':
             gen_elements()
         else:

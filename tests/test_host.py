@@ -163,3 +163,18 @@ def test_lobpcg_driver_on_numpy_ops(golden):
     lam, rel, its = lobpcg(ops, m, k, tol=1e-6, max_iter=1500, stall_window=10 ** 6)   # slow is not stalled
     assert np.all(rel[:k] <= 1e-6), (its, rel)
     assert np.allclose(np.sqrt(lam[:k]) / (2 * np.pi), w_ref[:k], rtol=1e-6)
+
+
+def test_modal_filters_match_reference(golden):
+    """FEM_Problem._filter_eigenvalues_1/2 (FEM.py:335-418) on a synthetic spectrum against the reference's output."""
+    import femol_b200 as F
+    g = golden('modal_filters')
+    mesh = F.mesh.rectangle_Q4(2., 2., 2, 2)
+    prob = F.FEM_Problem('modal', 'plate', mesh)
+    for k, fn in ((1, prob._filter_eigenvalues_1), (2, prob._filter_eigenvalues_2)):
+        w, v = fn(g['w'].copy(), g['v'].copy())
+        assert np.array_equal(w.shape, g['w%d' % k].shape)
+        assert np.allclose(w, g['w%d' % k], rtol=1e-14) and np.array_equal(v, g['v%d' % k])
+    plane = F.FEM_Problem('modal', 'plane', mesh)
+    with pytest.raises(TypeError):                      # the reference's mesh-mode filter returns None for plane models
+        plane._filter_eigenvalues_1(g['w'].copy(), g['v'][:, :18].copy())
