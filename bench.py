@@ -33,7 +33,7 @@ UNIT = 'SIMP iterations/s'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='femol', choices=['femol', 'reference'])
     ap.add_argument('--nx', type=int, default=2000)
