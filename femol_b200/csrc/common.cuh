@@ -160,3 +160,25 @@ static inline int femol_grid_for(int64_t n, int block, int sm_count, int waves =
 }
 
 int femol_sm_count();
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// A CG iteration is ~26 short kernels back to back in one stream (a CUDA graph); the ~1.8 us between the end of one
+// and the start of the next was 9 % of a SIMP step.  Kernels launched through femol_launch_pdl may be SCHEDULED
+// while their predecessor is still running; they execute FEMOL_PDL_SYNC() as their first statement, which lets
+// their own successor be scheduled and then waits until every predecessor grid has completed and its writes are
+// visible, so no global memory is touched early.  Without the launch attribute both instructions are no-ops.
+// FEMOL_PDL=0 disables the attribute.
+#define FEMOL_PDL_SYNC() asm volatile("griddepcontrol.launch_dependents;\n griddepcontrol.wait;\n" ::: "memory")
+
+bool femol_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t femol_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = femol_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}

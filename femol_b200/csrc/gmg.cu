@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(256)
 restrict_kernel(int64_t nxf64, int64_t nyf64, int64_t nxc64, int64_t nyc64, const uint8_t* __restrict__ ff,
                 const uint8_t* __restrict__ fc, const double* __restrict__ rf, double* __restrict__ rc,
                 const double* __restrict__ dinv_c, double omega, double* __restrict__ ec) {
+    FEMOL_PDL_SYNC();
     const int nxf = (int)nxf64, nyf = (int)nyf64, nxc = (int)nxc64, nyc = (int)nyc64;
     const int nn = (nxc + 1) * (nyc + 1);
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += gridDim.x * blockDim.x) {
@@ -295,6 +296,7 @@ template <int ND>
 __global__ void __launch_bounds__(256)
 prolong_add_kernel(int64_t nxf64, int64_t nyf64, int64_t nxc64, const uint8_t* __restrict__ ff,
                    const double* __restrict__ ec, const double* ef, double* out) {
+    FEMOL_PDL_SYNC();
     const int nxf = (int)nxf64, nyf = (int)nyf64, nxc = (int)nxc64;
     const int nn = (nxf + 1) * (nyf + 1);
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += gridDim.x * blockDim.x) {
@@ -889,14 +891,16 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, boo
                       : femol_apply_epilogue_launch(L.plan, L.vals, e, L.t, res, st);
         if (rc != FEMOL_OK) return rc;
         const bool coarse_regular = l + 1 != g->n_levels - 1;   // every smoothing level starts from omega Dinv r
-        restrict_kernel<ND><<<grid_for(C.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, C.ny, L.fixed, C.fixed, L.t, C.r,
-                                                                 coarse_regular ? C.dinv : nullptr, g->omega, C.e);
-        FEMOL_LAUNCH_CHECK();
+        FEMOL_CUDA_CHECK(femol_launch_pdl(restrict_kernel<ND>, dim3(grid_for(C.n_nodes)), dim3(256), 0, st, L.nx, L.ny, C.nx, C.ny,
+                                          (const uint8_t*)L.fixed, (const uint8_t*)C.fixed, (const double*)L.t, C.r,
+                                          (const double*)(coarse_regular ? C.dinv : nullptr), g->omega, C.e));
+        femol_count_launch();
         rc = vcycle<ND>(g, l + 1, C.r, C.e, st, coarse_regular);
         if (rc != FEMOL_OK) return rc;
         if (femol_apply_has_jacobi(L.plan, L.vals)) {
-            prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e, L.t);
-            FEMOL_LAUNCH_CHECK();
+            FEMOL_CUDA_CHECK(femol_launch_pdl(prolong_add_kernel<ND>, dim3(grid_for(L.n_nodes)), dim3(256), 0, st, L.nx, L.ny, C.nx,
+                                              (const uint8_t*)L.fixed, (const double*)C.e, (const double*)e, L.t));
+            femol_count_launch();
             // level 0 inside CG: the last kernel of the V-cycle also delivers r . z
             const femol_epilogue jac = {FEMOL_EPI_JACOBI, r, L.dinv, g->omega, rz_out, red_ws};
             if (rz_out && rz_fused) *rz_fused = true;

@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(VEC_THREADS)
 gpcg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ u,
             double* __restrict__ r, double* __restrict__ sc, double* __restrict__ red_ws,
             const double* __restrict__ dinv, double omega, double* __restrict__ z) {
+    FEMOL_PDL_SYNC();
     if (sc[S_DONE] != 0.0) return;
     __shared__ double s_red[32];
     const double rz = sc[S_RZN], pq = sc[S_PQ];
@@ -401,6 +402,7 @@ gpcg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ 
 // first: p = z ; else p = z + (rz_new / rz_old) p
 __global__ void __launch_bounds__(VEC_THREADS)
 gpcg_direction(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ sc, int first) {
+    FEMOL_PDL_SYNC();
     if (sc[S_DONE] != 0.0) return;
     const double beta = first ? 0.0 : sc[S_RZN] / sc[S_RZO];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -415,13 +417,14 @@ struct GpcgCtx {
 int gpcg_iteration(const GpcgCtx& c, cudaStream_t st) {
     int rc = femol_apply_launch(c.plan, c.vals, c.p, c.q, c.p, c.sc + S_PQ, c.red, st);
     if (rc != FEMOL_OK) return rc;
+    const double* cp = c.p; const double* cq = c.q;
     if (c.first_sweep_fused && c.plan->ndof == 2)
-        gpcg_update<2><<<c.ngrid, VEC_THREADS, 0, st>>>(c.n, c.p, c.q, c.u, c.r, c.sc, c.red, c.dinv0, c.omega0, c.z);
+        FEMOL_CUDA_CHECK(femol_launch_pdl(gpcg_update<2>, dim3(c.ngrid), dim3(VEC_THREADS), 0, st, c.n, cp, cq, c.u, c.r, c.sc, c.red, c.dinv0, c.omega0, c.z));
     else if (c.first_sweep_fused && c.plan->ndof == 6)
-        gpcg_update<6><<<c.ngrid, VEC_THREADS, 0, st>>>(c.n, c.p, c.q, c.u, c.r, c.sc, c.red, c.dinv0, c.omega0, c.z);
+        FEMOL_CUDA_CHECK(femol_launch_pdl(gpcg_update<6>, dim3(c.ngrid), dim3(VEC_THREADS), 0, st, c.n, cp, cq, c.u, c.r, c.sc, c.red, c.dinv0, c.omega0, c.z));
     else
-        gpcg_update<0><<<c.vgrid, VEC_THREADS, 0, st>>>(c.n, c.p, c.q, c.u, c.r, c.sc, c.red, nullptr, 0.0, nullptr);
-    FEMOL_LAUNCH_CHECK();
+        FEMOL_CUDA_CHECK(femol_launch_pdl(gpcg_update<0>, dim3(c.vgrid), dim3(VEC_THREADS), 0, st, c.n, cp, cq, c.u, c.r, c.sc, c.red, (const double*)nullptr, 0.0, (double*)nullptr));
+    femol_count_launch();
     bool rz_fused = false;
     rc = femol_gmg_vcycle_internal(c.gmg, c.r, c.z, st, c.sc + S_RZN, c.red, &rz_fused, c.first_sweep_fused);
     if (rc != FEMOL_OK) return rc;
@@ -429,8 +432,8 @@ int gpcg_iteration(const GpcgCtx& c, cudaStream_t st) {
         gpcg_dot<<<c.vgrid, VEC_THREADS, 0, st>>>(c.n, c.r, c.z, c.sc, c.red);
         FEMOL_LAUNCH_CHECK();
     }
-    gpcg_direction<<<c.vgrid, VEC_THREADS, 0, st>>>(c.n, c.z, c.p, c.sc, 0);
-    FEMOL_LAUNCH_CHECK();
+    FEMOL_CUDA_CHECK(femol_launch_pdl(gpcg_direction, dim3(c.vgrid), dim3(VEC_THREADS), 0, st, c.n, (const double*)c.z, c.p, (const double*)c.sc, 0));
+    femol_count_launch();
     return FEMOL_OK;
 }
 

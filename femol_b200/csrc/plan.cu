@@ -9,6 +9,7 @@
 #include <cub/device/device_scan.cuh>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -34,6 +35,15 @@ extern "C" int femol_device_count(void) {
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
+bool femol_pdl_enabled() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* env = getenv("FEMOL_PDL");
+        cached = (env && atoi(env) == 0) ? 0 : 1;
+    }
+    return cached == 1;
+}
+
 int femol_sm_count() {
     static int cached = 0;
     if (cached) return cached;

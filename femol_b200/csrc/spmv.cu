@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(256)
 spmv_block2_f32_kernel(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj_idx,
                        const float4* __restrict__ blk, const double* __restrict__ x, double* __restrict__ y,
                        const double* __restrict__ rhs, const double* __restrict__ dinv, double omega) {
+    FEMOL_PDL_SYNC();
     const int g = threadIdx.x % G;
     const int64_t node0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x / G;
@@ -145,9 +146,10 @@ int launch_block2(femol_plan_t p, const float* vals32, const double* x, double* 
     const int64_t cap = (int64_t)p->sm_count * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    spmv_block2_f32_kernel<G, MODE><<<(int)blocks, 256, 0, st>>>(p->n_nodes, p->adj_ptr, p->adj_idx,
-                                                                 reinterpret_cast<const float4*>(vals32), x, y, ep.rhs, ep.dinv, ep.omega);
-    FEMOL_LAUNCH_CHECK();
+    FEMOL_CUDA_CHECK(femol_launch_pdl(spmv_block2_f32_kernel<G, MODE>, dim3((unsigned)blocks), dim3(256), 0, st, p->n_nodes,
+                                      (const int32_t*)p->adj_ptr, (const int32_t*)p->adj_idx, reinterpret_cast<const float4*>(vals32),
+                                      x, y, ep.rhs, ep.dinv, ep.omega));
+    femol_count_launch();
     return FEMOL_OK;
 }
 

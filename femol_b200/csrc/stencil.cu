@@ -63,6 +63,7 @@ stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int
     constexpr int NPN = (PJ * PI + NTH - 1) / NTH;                    // patch nodes per thread (mask handling)
     extern __shared__ __align__(16) double s_mem[];
     __shared__ double s_red[32];
+    FEMOL_PDL_SYNC();
     const int npx = nx + 1;
     const int first = (cta0 + (int)blockIdx.x) * NT;
     const int tj0 = first / tiles_i, ti0 = first - tj0 * tiles_i;
@@ -272,10 +273,10 @@ int launch_stencil_c(femol_plan_t p, const femol_matrix_free* mf, const double* 
     const bool fused = n_cta <= max_grid;
     for (int64_t c0 = 0; c0 < n_cta; c0 += max_grid) {
         const int64_t nb = n_cta - c0 < max_grid ? n_cta - c0 : max_grid;
-        kern<<<(int)nb, TI * TJ / NPT, smem, st>>>(km, (int)mf->nx, (int)mf->ny, tiles_i, (int)n_tiles, (int)c0, mf->xpow, mf->fixed, x, y,
-                                             fused ? dot_with : nullptr, fused ? dot_out : nullptr, red_ws, ep.rhs, ep.dinv,
-                                             ep.omega);
-        FEMOL_LAUNCH_CHECK();
+        FEMOL_CUDA_CHECK(femol_launch_pdl(kern, dim3((unsigned)nb), dim3(TI * TJ / NPT), smem, st, km, (int)mf->nx, (int)mf->ny, tiles_i,
+                                          (int)n_tiles, (int)c0, mf->xpow, mf->fixed, x, y, fused ? dot_with : nullptr,
+                                          fused ? dot_out : nullptr, red_ws, ep.rhs, ep.dinv, ep.omega));
+        femol_count_launch();
     }
     if (!fused && dot_out) return femol_dot(p->n_nodes * p->ndof, y, dot_with, dot_out, red_ws, st);
     return FEMOL_OK;
