@@ -1056,7 +1056,7 @@ extern "C" int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t f
         g->cluster_size = 0;
         g->hint_iters = 0;
         const char* env_mb = getenv("FEMOL_GMG_CLUSTER_MB");
-        const double cluster_mb = env_mb ? atof(env_mb) : 0.7;   // measured on cfg 2 (it/s): 12 MB 46.6, 3 MB 49.0, 0.7 MB 49.4, off 49.5
+        const double cluster_mb = env_mb ? atof(env_mb) : 0.0;   // OFF by default: with PDL launches plain kernels win (cfg 2, it/s: off 62-67, 0.7 MB 60-63, 12 MB 47)
         const char* env_solo = getenv("FEMOL_GMG_SOLO_NODES");
         const long long solo_nodes = env_solo ? atoll(env_solo) : 700;
         if (g->nu == 1 && cluster_mb > 0) {

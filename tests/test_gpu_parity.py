@@ -802,3 +802,20 @@ def test_gmg_mid_size_plate_regular_levels(F):
     U_bj = p.solve_device()
     assert it_mg < p.solver_info['iterations'] // 2, (it_mg, p.solver_info)
     assert rel(U.cpu().numpy(), U_bj.cpu().numpy()) < 1e-4
+
+
+def test_cluster_vcycle_kernel_opt_in(F, monkeypatch):
+    """The thread-block-cluster kernel for the smallest multigrid levels is off by default (plain launches with
+    programmatic dependent launch measured faster); FEMOL_GMG_CLUSTER_MB switches it on.  Same solution, same
+    iteration count as the default path."""
+    out = {}
+    for mb in ('0', '0.7'):
+        monkeypatch.setenv('FEMOL_GMG_CLUSTER_MB', mb)
+        p, x = _gmg_problem(F, 90, 47, 'plane')
+        p.solver_rtol = 1e-10
+        p.assemble('K', X={'quad': x}, p=3)
+        p.preconditioner = 'gmg'
+        out[mb] = (p.solve_device().cpu().numpy().copy(), dict(p.solver_info))
+        assert out[mb][1]['converged']
+    assert abs(out['0'][1]['iterations'] - out['0.7'][1]['iterations']) <= 1
+    assert rel(out['0'][0], out['0.7'][0]) < 1e-8
