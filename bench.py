@@ -269,6 +269,9 @@ def run_gpu(args):
         spmv_kernel = 8 * nnz + 4 * nnzn + 4 * (d.n_nodes + 1) + 16 * n
         asm_survey = n_elem * (8 + 4 * (d.nn * d.ndof) ** 2) + 8 * nnz
         asm_kernel = 8 * nnz + 4 * (d.n_nodes + 1) + 4 * nnzn * 4 + 4 * nnzn + 8 * n_elem + d.n_nodes
+        grid_asm = bool(problem.structured_grid_shape())
+        if grid_asm:      # structured grid: scatter pattern derived from coordinates, a pure write stream
+            asm_kernel = 8 * nnz + 4 * (d.n_nodes + 1) + 8 * n_elem + d.n_nodes
         Eb, pe = problem._element_matrices('K', False)
         vals = torch.empty(nnz, dtype=torch.float64, device='cuda')
         mask = problem._fixed_mask()
@@ -325,9 +328,9 @@ def run_gpu(args):
             roofline = dict(spmv_csr)
             roofline['launches_in_timed_region'] = fine_spmv
             roofline['share_of_step'] = fine_spmv * t_spmv / dt if dt > 0 else None
-        roofline_asm = {'kernel': 'femol_assemble = density_power + assemble_slots_kernel<2,4,9,4>', 'bound': 'hbm',
+        roofline_asm = {'kernel': 'femol_assemble = density_power + ' + ('assemble_grid_kernel<2,false> (thread per node, smem-staged coalesced stores)' if grid_asm else 'assemble_slots_kernel<2,4,9,4>'), 'bound': 'hbm',
                         'achieved': asm_survey / t_asm / 1e9, 'peak': peak, 'unit': 'GB/s',
-                        'frac': asm_survey / t_asm / 1e9 / peak, 'traffic': 938.0e6,
+                        'frac': asm_survey / t_asm / 1e9 / peak, 'traffic': None if grid_asm else 938.0e6,
                         'algorithmic_bytes_per_launch': asm_survey, 'avg_launch_s': t_asm,
                         'kernel_compulsory_bytes_per_launch': asm_kernel,
                         'frac_on_kernel_bytes': asm_kernel / t_asm / 1e9 / peak,

@@ -235,6 +235,9 @@ class FEM_Problem(object):
         if self._dev is None:
             self._dev = _Device(self.mesh, self.N_dof)
             self.mesh._femol_device = self._dev      # Mesh.stress_from_displacement reuses the plan
+            shape = self.structured_grid_shape()
+            if shape:                                # assembly derives the scatter pattern from grid coordinates
+                _lib.call('femol_plan_set_grid', self._dev.plan, shape[0], shape[1])
         return self._dev
 
     def _bc_key(self):

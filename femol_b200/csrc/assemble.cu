@@ -306,6 +306,131 @@ int launch_assemble(femol_plan_t p, const double* e_base, int base_pe, const dou
     return FEMOL_OK;
 }
 
+
+// ---- structured rectangle_Q4 grids with a shared element matrix (femol_plan_set_grid) ---------------------------------
+// One thread per node.  Which elements two nodes share, and with which local indices, follows from their grid
+// coordinates, so nothing but the four element weights and the Dirichlet mask is read: the kernel is a pure 576 MB
+// write stream on cfg 2 instead of three dependent gather levels (adjacency -> source list -> x^p).  Contributions
+// are added in ascending element order, exactly like the list kernels: the values are bit-identical.
+template <int ND, bool COAT>
+__global__ void __launch_bounds__(128)
+assemble_grid_kernel(int nx, int ny, const int32_t* __restrict__ adj_ptr, const double* __restrict__ e_base,
+                     const double* __restrict__ e_coat, const double* __restrict__ xpow, const uint8_t* __restrict__ fixed,
+                     double* __restrict__ vals) {
+    constexpr int S = 4 * ND, S2 = S * S;
+    constexpr int T = ND == 2 ? 1 : 4;          // threads per node (they split the nine neighbours)
+    constexpr int NPP = 128 / T;                // nodes per CTA pass
+    extern __shared__ __align__(16) double s_dyn[];
+    double* s_mat = s_dyn;                      // [S2] base | [S2] coat
+    double* s_out = s_dyn + (COAT ? 2 : 1) * S2;  // the pass's contiguous slice of vals: <= NPP * 9 * ND * ND doubles
+    for (int t = threadIdx.x; t < S2; t += blockDim.x) { s_mat[t] = e_base[t]; if (COAT) s_mat[S2 + t] = e_coat[t]; }
+    const int npx = nx + 1, n_nodes = npx * (ny + 1);
+    const int ln = threadIdx.x / T, sub = threadIdx.x - ln * T;
+    for (int i0 = blockIdx.x * NPP; i0 < n_nodes; i0 += gridDim.x * NPP) {
+        __syncthreads();    // element matrices staged / previous pass copied out
+        const int i1 = min(i0 + NPP, n_nodes);
+        const int pb0 = __ldg(&adj_ptr[i0]), pb1 = __ldg(&adj_ptr[i1]);
+        const int i = i0 + ln;
+        if (i < i1) {
+            const int yi = i / npx, xi = i - yi * npx;
+            // weights of the four elements around the node, (ex, ey) -> element (xi - 1 + ex, yi - 1 + ey); absent: flagged
+            double w[2][2]; bool in[2][2];
+#pragma unroll
+            for (int ex = 0; ex < 2; ++ex)
+#pragma unroll
+                for (int ey = 0; ey < 2; ++ey) {
+                    const int gx = xi - 1 + ex, gy = yi - 1 + ey;
+                    in[ex][ey] = gx >= 0 && gx < nx && gy >= 0 && gy < ny;
+                    w[ex][ey] = (in[ex][ey] && xpow) ? __ldg(&xpow[gx * ny + gy]) : 1.0;
+                }
+            const uint32_t fr = fixed ? __ldg(&fixed[i]) : 0u;
+            const int cx = 1 + (xi > 0) + (xi < nx), cy = 1 + (yi > 0) + (yi < ny);   // neighbours per direction
+            const int len = cx * cy;
+            double* out = s_out + (size_t)ND * ND * (__ldg(&adj_ptr[i]) - pb0);
+#pragma unroll
+            for (int dj = -1; dj <= 1; ++dj) {
+                if (yi + dj < 0 || yi + dj > ny) continue;
+#pragma unroll
+                for (int di = -1; di <= 1; ++di) {
+                    if (xi + di < 0 || xi + di > nx) continue;
+                    if (T > 1 && ((dj + 1) * 3 + di + 1) % T != sub) continue;
+                    // position of this neighbour in the node's sorted adjacency
+                    const int k = ((dj + 1) - (yi == 0)) * cx + (di + 1) - (xi == 0);
+                    double acc[ND][ND];
+#pragma unroll
+                    for (int a = 0; a < ND; ++a)
+#pragma unroll
+                        for (int b = 0; b < ND; ++b) acc[a][b] = 0.0;
+                    // shared elements: ex in {di, di + 1} & {0, 1}, ey likewise; ascending element id = ex-major
+#pragma unroll
+                    for (int ex = 0; ex < 2; ++ex) {
+                        if (ex != di && ex != di + 1) continue;
+#pragma unroll
+                        for (int ey = 0; ey < 2; ++ey) {
+                            if (ey != dj && ey != dj + 1) continue;
+                            if (!in[ex][ey]) continue;
+                            // local indices in that element (Q4 order (0,0) (1,0) (1,1) (0,1)): node i sits at (1-ex, 1-ey)
+                            const int ax = 1 - ex, ay = 1 - ey, bx = ax + di, by = ay + dj;
+                            const int la = ay == 0 ? ax : 3 - ax, lb = by == 0 ? bx : 3 - bx;
+                            const double* eb = s_mat + la * ND * S + lb * ND;
+                            const double ww = w[ex][ey];
+#pragma unroll
+                            for (int a = 0; a < ND; ++a)
+#pragma unroll
+                                for (int b = 0; b < ND; ++b)
+                                    acc[a][b] += COAT ? eb[a * S + b] + ww * eb[S2 + a * S + b] : ww * eb[a * S + b];
+                        }
+                    }
+                    const uint32_t fc = fixed ? __ldg(&fixed[i + dj * npx + di]) : 0u;
+                    if (fr | fc) {  // FEM.py:902-930: fixed rows and columns zeroed, unit diagonal
+                        const bool diag = di == 0 && dj == 0;
+#pragma unroll
+                        for (int a = 0; a < ND; ++a)
+#pragma unroll
+                            for (int b = 0; b < ND; ++b)
+                                if (((fr >> a) | (fc >> b)) & 1u) acc[a][b] = (diag && a == b) ? 1.0 : 0.0;
+                    }
+#pragma unroll
+                    for (int a = 0; a < ND; ++a) {
+                        double2* o2 = reinterpret_cast<double2*>(out + (size_t)a * len * ND + (size_t)k * ND);
+#pragma unroll
+                        for (int b = 0; b < ND; b += 2) o2[b >> 1] = make_double2(acc[a][b], acc[a][b + 1]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // the slice is contiguous in vals: coalesced streaming stores
+        const int n2 = (pb1 - pb0) * ND * ND / 2;
+        double2* g2 = reinterpret_cast<double2*>(vals + (size_t)ND * ND * pb0);
+        const double2* s2 = reinterpret_cast<const double2*>(s_out);
+        for (int t = threadIdx.x; t < n2; t += blockDim.x) __stcs(&g2[t], s2[t]);
+    }
+}
+
+template <int ND>
+int launch_grid(femol_plan_t p, const double* e_base, const double* e_coat, const double* xpow, const uint8_t* fixed,
+                double* vals, cudaStream_t st) {
+    constexpr int NPP = 128 / (ND == 2 ? 1 : 4);
+    const size_t smem = ((size_t)(e_coat ? 2 : 1) * 16 * ND * ND + (size_t)NPP * 9 * ND * ND) * sizeof(double);
+    int64_t grid = (p->n_nodes + NPP - 1) / NPP;
+    const int64_t cap = (int64_t)p->sm_count * 16;
+    if (grid > cap) grid = cap;
+    if (e_coat) {
+        auto kern = assemble_grid_kernel<ND, true>;
+        static bool configured = false;
+        if (!configured) { FEMOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024)); configured = true; }
+        kern<<<(int)grid, 128, smem, st>>>((int)p->grid_nx, (int)p->grid_ny, p->adj_ptr, e_base, e_coat, xpow, fixed, vals);
+    } else {
+        auto kern = assemble_grid_kernel<ND, false>;
+        static bool configured = false;
+        if (!configured) { FEMOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024)); configured = true; }
+        kern<<<(int)grid, 128, smem, st>>>((int)p->grid_nx, (int)p->grid_ny, p->adj_ptr, e_base, nullptr, xpow, fixed, vals);
+    }
+    FEMOL_LAUNCH_CHECK();
+    return FEMOL_OK;
+}
+
 }  // namespace
 
 extern "C" int femol_assemble(femol_plan_t p, const double* e_base, int base_per_elem, const double* e_coat,
@@ -319,6 +444,10 @@ extern "C" int femol_assemble(femol_plan_t p, const double* e_base, int base_per
         density_power<<<femol_grid_for(p->n_elem, 256, p->sm_count), 256, 0, st>>>(p->n_elem, x, expo, xpow_ws);
         FEMOL_LAUNCH_CHECK();
         xpow = xpow_ws;
+    }
+    if (p->grid_nx > 0 && p->nn == 4 && !base_per_elem && !(e_coat && coat_per_elem)) {   // structured grid, shared Ke
+        if (p->ndof == 2) return launch_grid<2>(p, e_base, e_coat, xpow, fixed, vals, st);
+        if (p->ndof == 6) return launch_grid<6>(p, e_base, e_coat, xpow, fixed, vals, st);
     }
 #define ASM_CASE(ND, NN) \
     if (p->ndof == ND && p->nn == NN) return launch_assemble<ND, NN>(p, e_base, base_per_elem, e_coat, coat_per_elem, xpow, fixed, vals, st);

@@ -64,6 +64,7 @@ struct femol_plan {
     int ell_width;      // 4, 8 or 0 (a node pair with more than 8 contributing elements: lists only)
     int sm_count;
     femol_matrix_free* mf;  // host struct, optional (femol_plan_set_matrix_free)
+    int64_t grid_nx, grid_ny;  // > 0: the mesh is an nx x ny rectangle_Q4 grid (femol_plan_set_grid)
 };
 
 // Deterministic grid reduction scratch: FEMOL_RED_SLOTS partial slots + a ticket counter.

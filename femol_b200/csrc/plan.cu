@@ -405,3 +405,41 @@ extern "C" int femol_plan_export_scatter_map(femol_plan_t p, int32_t* map, void*
     FEMOL_LAUNCH_CHECK();
     return FEMOL_OK;
 }
+
+namespace {
+__global__ void check_grid_conn(int64_t nx, int64_t ny, const int32_t* __restrict__ conn, int* __restrict__ bad) {
+    const int64_t ne = nx * ny;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / ny, j = e - i * ny;
+        const int64_t a = i + (nx + 1) * j;
+        if (conn[4 * e] != a || conn[4 * e + 1] != a + 1 || conn[4 * e + 2] != a + nx + 2 || conn[4 * e + 3] != a + nx + 1) *bad = 1;
+    }
+}
+}  // namespace
+
+// Declares the mesh to be an nx x ny rectangle_Q4 grid (nodes x-fastest, element e = i*ny + j with nodes
+// [a, a+1, a+nx+2, a+nx+1], a = i + (nx+1) j: mesh.py:852-860 / meshzoo.rectangle_quad) after VERIFYING the
+// connectivity on the device.  femol_assemble then derives the contributing elements of every node pair from grid
+// coordinates instead of reading the source lists.  Synchronous (one flag read); nx = 0 clears.
+extern "C" int femol_plan_set_grid(femol_plan_t p, int64_t nx, int64_t ny) {
+    FEMOL_REQUIRE(p, "femol_plan_set_grid: null plan");
+    p->grid_nx = p->grid_ny = 0;
+    if (nx <= 0 || ny <= 0) return FEMOL_OK;
+    FEMOL_REQUIRE(p->nn == 4 && p->n_elem == nx * ny && p->n_nodes == (nx + 1) * (ny + 1) && p->n_nodes < (int64_t)1 << 25 && nx >= 1,
+                  "femol_plan_set_grid: plan is not an nx x ny 4-node grid (or has more than 2^25 nodes)");
+    int* d_bad = nullptr;
+    FEMOL_CUDA_CHECK(cudaMalloc(&d_bad, sizeof(int)));
+    FEMOL_CUDA_CHECK(cudaMemset(d_bad, 0, sizeof(int)));
+    check_grid_conn<<<femol_grid_for(p->n_elem, 256, p->sm_count), 256>>>(nx, ny, p->conn, d_bad);
+    FEMOL_LAUNCH_CHECK();
+    int bad = 0;
+    const cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d_bad);
+    FEMOL_CUDA_CHECK(e);
+    if (bad) {
+        femol_set_error("femol_plan_set_grid: connectivity is not in rectangle_Q4 order");
+        return FEMOL_E_ARG;
+    }
+    p->grid_nx = nx; p->grid_ny = ny;
+    return FEMOL_OK;
+}

@@ -106,6 +106,12 @@ int femol_spmv(femol_plan_t plan, const double* vals, const double* x, double* y
 int femol_spmv_csr(int64_t n_rows, const int32_t* indptr, const int32_t* indices, const double* vals,
                    const double* x, double* y, void* stream);
 
+/* Declares (and verifies on the device) that the plan's mesh is an nx x ny rectangle_Q4 grid: nodes x-fastest, element
+ * e = i*ny + j with nodes [a, a+1, a+nx+2, a+nx+1], a = i + (nx+1) j (mesh.py:852-860).  femol_assemble then derives the
+ * elements shared by a node pair from grid coordinates instead of reading the scatter lists (bit-identical values).
+ * Synchronous; nx = 0 clears; FEMOL_E_ARG if the connectivity is in another order. */
+int femol_plan_set_grid(femol_plan_t plan, int64_t nx, int64_t ny);
+
 /* Matrix-free K for the solvers on structured rectangle_Q4 meshes (nodes x-fastest, element e = i*ny + j):
  * declares that the value array `vals` equals sum_e (xpow_e * e_base [or e_base + xpow_e * e_coat]) with the
  * Dirichlet mask `fixed` applied — i.e. the arguments of the femol_assemble call that produced it.  femol_pcg /

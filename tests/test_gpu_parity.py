@@ -819,3 +819,29 @@ def test_cluster_vcycle_kernel_opt_in(F, monkeypatch):
         assert out[mb][1]['converged']
     assert abs(out['0'][1]['iterations'] - out['0.7'][1]['iterations']) <= 1
     assert rel(out['0'][0], out['0.7'][0]) < 1e-8
+
+
+@pytest.mark.parametrize('nx,ny,model,coating', [(17, 9, 'plane', False), (12, 7, 'plane', True), (9, 5, 'plate', False), (1, 1, 'plane', False),
+                                                 (64, 3, 'plane', False)])
+def test_grid_assembly_is_bit_identical_to_list_assembly(F, nx, ny, model, coating):
+    """femol_plan_set_grid: the assembly derives the scatter pattern from grid coordinates instead of reading the
+    source lists; same contributions in the same order, so the values are bit-identical (K, M, with BCs, coating)."""
+    import torch
+    p, x = _gmg_problem(F, nx, ny, model, coating)
+    d = p.device
+    out = {}
+    for grid in (True, False):
+        F._lib.call('femol_plan_set_grid', d.plan, nx if grid else 0, ny if grid else 0)
+        p.assemble('K', X={'quad': x}, p=3)
+        p.assemble('M', X={'quad': x}, q=1)
+        out[grid] = (p.K_values.clone(), p.M_values.clone())
+    assert torch.equal(out[True][0], out[False][0]) and torch.equal(out[True][1], out[False][1])
+    # a mesh whose cells are in another order is refused (the check runs on the device)
+    mesh = F.mesh.rectangle_Q4(float(nx), float(ny), nx, ny)
+    if nx * ny > 1:
+        cells = np.asarray(mesh.cells['quad'])[::-1].copy()
+        m2 = F.Mesh(mesh.points, {'quad': cells})
+        p2 = F.FEM_Problem('displacement', 'plane', m2)
+        assert p2.structured_grid_shape() is None
+        with pytest.raises(F._lib.FemolError):
+            F._lib.call('femol_plan_set_grid', p2.device.plan, nx, ny)
