@@ -845,3 +845,34 @@ def test_grid_assembly_is_bit_identical_to_list_assembly(F, nx, ny, model, coati
         assert p2.structured_grid_shape() is None
         with pytest.raises(F._lib.FemolError):
             F._lib.call('femol_plan_set_grid', p2.device.plan, nx, ny)
+
+
+def test_modal_mid_size_against_shift_invert(F):
+    """SURVEY 8(d) cfg 4 at 48 x 48 (14 k dof): NAFEMS FV13-like simply supported plate, lowest 6 modes by LOBPCG with
+    the multigrid-CG preconditioner against scipy's shift-invert Lanczos (`eigsh(sigma=0)`, the reference's 'sparse'
+    path, FEM.py:234) on the same assembled pencil restricted to the free, non-drilling dofs."""
+    import scipy.sparse.linalg as sla
+    n = 48
+    mesh = F.mesh.rectangle_Q4(10., 10., n, n)
+    p = F.FEM_Problem('modal', 'plate', mesh)
+    p.define_materials(F.materials.IsotropicMaterial(200e9, 0.3, 8000)); p.define_tensors(0.05)
+    p.add_fixed_domain(F.domains.inside_box([[0, 10.]], [[0, 10.]]), ddls=[0, 1, 5])
+    p.add_fixed_domain(F.domains.inside_box([0, 10.], [[0, 10.]]), ddls=[2, 4])
+    p.add_fixed_domain(F.domains.inside_box([[0, 10.]], [0, 10.]), ddls=[2, 3])
+    p.n_modes = 6
+    p.modal_tol = 1e-8
+    w, v = p.solve(verbose=False)
+    assert p.solver_info['iterations'] < p.modal_max_iter
+    K, M = p.K, p.M
+    keep = np.ones(K.shape[0], bool)
+    keep[p.fixed_dofs()] = False
+    keep[5::6] = False
+    Kf = K[keep][:, keep].tocsc(); Mf = M[keep][:, keep].tocsc()
+    lam = sla.eigsh(Kf, k=6, M=Mf, sigma=0, which='LM', return_eigenvectors=False)
+    ref = np.sort(np.sqrt(lam) / (2 * np.pi))
+    assert np.allclose(np.sort(w)[:6], ref, rtol=1e-6), (w, ref)
+    # NAFEMS FV13 (thin-plate target values 2.377, 5.942, 5.942, 9.507, 11.884, 11.884 Hz): within 1 % on this mesh
+    assert np.allclose(np.sort(w)[:6], [2.377, 5.942, 5.942, 9.507, 11.884, 11.884], rtol=1e-2)
+    # M-orthonormal modes (test_modal_solver.py:7-22)
+    G = v[:6] @ (M @ v[:6].T)
+    assert np.allclose(G, np.eye(6), atol=1e-6)
