@@ -56,6 +56,8 @@ def cfg4(scale, iters=3):
     p.add_fixed_domain(F.domains.inside_box([[0, 10.]], [0, 10.]), ddls=[2, 3])
     p.n_modes = 6
     p.modal_inner_iters = 600
+    p.modal_gmg_iters = int(os.environ.get('MODAL_GMG_ITERS', p.modal_gmg_iters))
+    p.modal_inner_tol = float(os.environ.get('MODAL_INNER_TOL', p.modal_inner_tol))
     p.modal_tol = 1e-8
     t0 = sync(); w, v = p.solve(verbose=False); t1 = sync()
     out = {'config': 'cfg4 SIMP_VIBE plate %dx%d' % (n, n), 'ndof': 6 * (n + 1) ** 2, 'nnz': p.device.nnz,
