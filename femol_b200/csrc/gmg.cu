@@ -221,6 +221,72 @@ coarsen_elements(int64_t nxf, int64_t nyf, int64_t nxc, int64_t nyc, const doubl
     }
 }
 
+// Galerkin coarsening of per-element matrices, register / shuffle version (levels >= 1 -> next).  The parent is
+// sum_c P_c^T K_c P_c with P_c = W_c (x) I_ND (W_c: 4 x 4 bilinear weights of the child's nodes in the parent), so
+// every dof pair (da, db) is an independent 4 x 4 triple product W_c^T K_c^{da,db} W_c.  A warp owns a coarse element;
+// lane = (dd slot (4), r (4), q half (2)): stage 1 forms T[a = r][q] = sum_b K_c[(r,da),(b,db)] W_c[b][q] from four
+// global loads, stage 2 forms out[p = r][q] = sum_a W_c[a][r] T[a][q] with four shuffles per q.  No shared memory,
+// ~10 x fewer instructions than the generic kernel above (which stays for level 0, where child matrices are
+// synthesised from the shared element matrix).
+__device__ __forceinline__ double bilinear(int node, double s, double t) {
+    return node == 0 ? (1 - s) * (1 - t) : node == 1 ? s * (1 - t) : node == 2 ? s * t : (1 - s) * t;
+}
+
+template <int ND>
+__global__ void __launch_bounds__(128)
+coarsen_elements_fast(int nxf, int nyf, int nxc, int nyc, const double* __restrict__ child_ke,
+                      const uint8_t* __restrict__ fixed_f, double* __restrict__ out) {
+    constexpr int S = 4 * ND, S2 = S * S, NDD = ND * ND;
+    const int lane = threadIdx.x & 31;
+    const int ddl = lane >> 3, r = (lane >> 1) & 3, qh = lane & 1;
+    const int nec = nxc * nyc;
+    const int warp0 = blockIdx.x * 4 + (threadIdx.x >> 5), nwarps = gridDim.x * 4;
+    for (int E = warp0; E < nec; E += nwarps) {
+        const int I = E / nyc, J = E - I * nyc;
+        const bool fullx = 2 * I + 1 < nxf, fully = 2 * J + 1 < nyf;
+        for (int dd0 = 0; dd0 < NDD; dd0 += 4) {
+            const int dd = dd0 + ddl;            // NDD is a multiple of 4 (4 or 36): every lane is active
+            const int da = dd / ND, db = dd - da * ND;
+            double acc0 = 0.0, acc1 = 0.0;
+            for (int ca = 0; ca <= (fullx ? 1 : 0); ++ca)
+                for (int cb = 0; cb <= (fully ? 1 : 0); ++cb) {
+                    const int ci = 2 * I + ca, cj = 2 * J + cb;
+                    const size_t c = (size_t)ci * nyf + cj;                  // fine element id
+                    const int n00 = ci + (nxf + 1) * cj;
+                    const int cn[4] = {n00, n00 + 1, n00 + nxf + 2, n00 + nxf + 1};
+                    // parametric position of the child's local nodes inside the parent: (s, t) in {0, 1/2, 1}
+                    const double s0 = fullx ? 0.5 * ca : 0.0, s1 = fullx ? 0.5 * (ca + 1) : 1.0;
+                    const double t0 = fully ? 0.5 * cb : 0.0, t1 = fully ? 0.5 * (cb + 1) : 1.0;
+                    const double ps[4] = {s0, s1, s1, s0}, pt[4] = {t0, t0, t1, t1};
+                    // stage 1: T[a = r][q], q = 2 qh, 2 qh + 1  (rows / columns of fixed fine dofs are zero)
+                    const uint32_t fr = fixed_f ? fixed_f[cn[r]] : 0u;
+                    double T0 = 0.0, T1 = 0.0;
+                    const double* krow = child_ke + c * S2 + (size_t)(r * ND + da) * S + db;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const uint32_t fb = fixed_f ? fixed_f[cn[b]] : 0u;
+                        double k = __ldg(krow + b * ND);
+                        if (((fr >> da) | (fb >> db)) & 1u) k = 0.0;
+                        T0 = fma(k, bilinear(2 * qh, ps[b], pt[b]), T0);
+                        T1 = fma(k, bilinear(2 * qh + 1, ps[b], pt[b]), T1);
+                    }
+                    // stage 2: out[p = r][q] += sum_a W[a][r] T[a][q]   (T[a][q] lives in lane (ddl, a, qh))
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int src = (ddl << 3) | (a << 1) | qh;
+                        const double ta0 = __shfl_sync(0xffffffffu, T0, src), ta1 = __shfl_sync(0xffffffffu, T1, src);
+                        const double wa = bilinear(r, ps[a], pt[a]);
+                        acc0 = fma(wa, ta0, acc0);
+                        acc1 = fma(wa, ta1, acc1);
+                    }
+                }
+            double* o = out + (size_t)E * S2 + (size_t)(r * ND + da) * S + db;
+            o[(2 * qh) * ND] = acc0;
+            o[(2 * qh + 1) * ND] = acc1;
+        }
+    }
+}
+
 // ---- transfer operators ---------------------------------------------------------------------------------------
 // 1-D weight of fine node c + dc in the restriction onto the coarse node centred at fine index c (n fine cells):
 // the transpose of cmap1d.  c is even except for the last node of an odd grid, which has no half-weight neighbours.
@@ -1088,6 +1154,8 @@ extern "C" int femol_gmg_setup(femol_gmg* g, const double* e_base, const double*
     cudaStream_t st = (cudaStream_t)stream;
     const int nd = g->nd;
     g->lv[0].vals = const_cast<double*>(fine_vals);
+    const char* env_old = getenv("FEMOL_GMG_OLD_COARSEN");
+    const bool fast_coarsen = !(env_old && atoi(env_old) != 0);
     for (int l = 1; l < g->n_levels; ++l) {
         Level& F = g->lv[l - 1];
         Level& C = g->lv[l];
@@ -1098,12 +1166,14 @@ extern "C" int femol_gmg_setup(femol_gmg* g, const double* e_base, const double*
             if (l == 1) {
                 child_images<2><<<2, 256, 0, st>>>(e_base, e_coat, g->child_g);
                 coarsen_elements<2, true><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, nullptr, e_base, e_coat, xpow, F.fixed, g->child_g, C.ke);
-            } else coarsen_elements<2, false><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, F.ke, nullptr, nullptr, nullptr, F.fixed, nullptr, C.ke);
+            } else if (fast_coarsen) coarsen_elements_fast<2><<<(int)blocks, 128, 0, st>>>((int)F.nx, (int)F.ny, (int)C.nx, (int)C.ny, F.ke, F.fixed, C.ke);
+            else coarsen_elements<2, false><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, F.ke, nullptr, nullptr, nullptr, F.fixed, nullptr, C.ke);
         } else {
             if (l == 1) {
                 child_images<6><<<18, 256, 0, st>>>(e_base, e_coat, g->child_g);
                 coarsen_elements<6, true><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, nullptr, e_base, e_coat, xpow, F.fixed, g->child_g, C.ke);
-            } else coarsen_elements<6, false><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, F.ke, nullptr, nullptr, nullptr, F.fixed, nullptr, C.ke);
+            } else if (fast_coarsen) coarsen_elements_fast<6><<<(int)blocks, 128, 0, st>>>((int)F.nx, (int)F.ny, (int)C.nx, (int)C.ny, F.ke, F.fixed, C.ke);
+            else coarsen_elements<6, false><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, F.ke, nullptr, nullptr, nullptr, F.fixed, nullptr, C.ke);
         }
         FEMOL_LAUNCH_CHECK();
         int rc = femol_assemble(C.plan, C.ke, 1, nullptr, 0, nullptr, 1.0, C.fixed, nullptr, C.vals, st);

@@ -876,3 +876,23 @@ def test_modal_mid_size_against_shift_invert(F):
     # M-orthonormal modes (test_modal_solver.py:7-22)
     G = v[:6] @ (M @ v[:6].T)
     assert np.allclose(G, np.eye(6), atol=1e-6)
+
+
+@pytest.mark.parametrize('nx,ny,model', [(90, 47, 'plane'), (64, 64, 'plane'), (37, 19, 'plate')])
+def test_fast_galerkin_coarsening_matches_generic(F, monkeypatch, nx, ny, model):
+    """The register / shuffle Galerkin coarsening of the levels >= 1 against the generic shared-memory kernel
+    (FEMOL_GMG_OLD_COARSEN=1): same hierarchy up to rounding -> same iteration count, same solution.  Odd sizes
+    exercise the half-width parents, the clamped edge the Dirichlet masking."""
+    out = {}
+    for old in ('1', '0'):
+        monkeypatch.setenv('FEMOL_GMG_OLD_COARSEN', old)
+        p, _ = _gmg_problem(F, nx, ny, model)
+        i, j = np.divmod(np.arange(nx * ny), ny)
+        x = 0.55 + 0.45 * np.sin(2 * np.pi * i / nx) * np.cos(2 * np.pi * j / ny)
+        p.solver_rtol = 1e-9 if model == 'plane' else 1e-7
+        p.assemble('K', X={'quad': x}, p=3)
+        p.preconditioner = 'gmg'
+        out[old] = (p.solve_device().cpu().numpy().copy(), dict(p.solver_info))
+        assert out[old][1]['converged']
+    assert abs(out['0'][1]['iterations'] - out['1'][1]['iterations']) <= 1, (out['0'][1], out['1'][1])
+    assert rel(out['0'][0], out['1'][0]) < 1e-6
