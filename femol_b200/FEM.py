@@ -166,6 +166,7 @@ class FEM_Problem(object):
         self._gmg_ws = None
         self._K_scaled = False
         self._mf_refs = None  # keeps the tensors the plan's matrix-free descriptor borrows alive
+        self._variable_core = False   # K / M came from assemble_variable_core (per-element laminates)
 
     def __del__(self):
         try:
@@ -338,6 +339,69 @@ class FEM_Problem(object):
                 _lib.call('femol_plan_set_matrix_free', d.plan, 0, 0, None, None, None, None, None)
         return vals
 
+    # ---- variable-core laminates (FEM.py:697-731, 873-896) -------------------------------------------------
+    def _variable_core_tensors(self, zc, h_min):
+        """Per-element [A, D, G, B] blocks (n_elem x 31) of the base and of the coating laminate.  For zc > h_min
+        the base laminate (full ply list, symetric=False) sits at z = -h/2 + hA0/2 and the coating at
+        +h/2 - hA1/2 with h = zc + hA0 + hA1; below, the unshifted base laminate alone.  A shift c of a laminate
+        changes its tensors by B = B0 + c A, D = D0 + 2 c B0 + c^2 A (A and G do not move), which vectorises the
+        reference's per-element `Layup(...)` construction."""
+        from .elements import pack_tensors
+        lb, lc = self.layups[0], self.layups[1]
+        zc = np.asarray(zc, dtype=np.float64)
+        above = zc > h_min
+        h = zc + lb.hA + lc.hA
+        out = []
+        for lay, mat, shift in ((lb, self.materials[0], np.where(above, -h / 2 + lb.hA / 2, 0.0)),
+                                (lc, self.materials[1], np.where(above, h / 2 - lc.hA / 2, 0.0))):
+            base = Layup(mat, plies=lay.angles, symetric=False)
+            A, B0, D0, G = (np.asarray(base.A_mat, float), np.asarray(base.B_mat, float), np.asarray(base.D_mat, float),
+                            np.asarray(base.G_mat, float))
+            c = shift[:, None, None]
+            T = np.zeros((zc.shape[0], 31))
+            T[:, 0:9] = np.broadcast_to(A, (zc.shape[0], 3, 3)).reshape(-1, 9)
+            T[:, 9:18] = (D0[None] + 2 * c * B0[None] + c * c * A[None]).reshape(-1, 9)
+            T[:, 18:22] = np.broadcast_to(G, (zc.shape[0], 2, 2)).reshape(-1, 4)
+            T[:, 22:31] = (B0[None] + c * A[None]).reshape(-1, 9)
+            out.append(T)
+        out[1][~above] = 0.0
+        return out[0], out[1], above
+
+    def assemble_variable_core(self, which, h_min=0):
+        """K or M from the per-element core heights `mesh.cell_data['zc']` (the data `solve(solve_from_zc=True)`
+        assembles, FEM.py:208, 226-227): element = base part + (zc > h_min) * coating part, through the ordinary
+        assembly kernel with per-element matrices and the 0/1 indicator as the 'density'."""
+        d = self.device
+        ctype = self.mesh.contains[0]
+        zc = np.asarray(self.mesh.cell_data['zc'][ctype], dtype=np.float64)
+        Tb, Tc, above = self._variable_core_tensors(zc, h_min)
+        size = d.nn * self.N_dof
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(d.dev)
+        if which == 'K':
+            E = []
+            for T in (Tb, Tc):
+                out = torch.empty((d.n_elem, size, size), dtype=torch.float64, device=d.dev)
+                t_dev = up(T)            # named: a temporary would be recycled by the caching allocator mid-call
+                _lib.call('femol_ke_batch_var', d.etype, self.N_dof, d.n_elem, _lib.ptr(d.xy), _lib.ptr(d.conn), _lib.ptr(t_dev), 0,
+                          _lib.ptr(out), _lib.stream())
+                E.append(out)
+            self.assemble('F')
+        else:
+            E = [elements.me_batch_device(d.etype, self.N_dof, d.xy, d.conn,
+                                          elements.mass_tensor(d.etype, self.N_dof, mat, ho))
+                 for mat, ho in ((self.materials[0], self.ho), (self.materials[1], self.coat_ho))]
+        vals = torch.empty(d.nnz, dtype=torch.float64, device=d.dev)
+        xpow = d.xpow if which == 'K' else d.xpow_m
+        indicator, mask = up(above.astype(np.float64)), self._fixed_mask()
+        _lib.call('femol_assemble', d.plan, _lib.ptr(E[0]), 1, _lib.ptr(E[1]), 1, _lib.ptr(indicator), 1.0,
+                  _lib.ptr(mask), _lib.ptr(xpow), _lib.ptr(vals), _lib.stream())
+        self._variable_core = True
+        if which == 'K':
+            self._Kv, self._K_host, self._gmg_stale, self._K_scaled = vals, None, True, False
+            _lib.call('femol_plan_set_matrix_free', d.plan, 0, 0, None, None, None, None, None)
+        else:
+            self._Mv, self._M_host = vals, None
+
     # ---- assembly -----------------------------------------------------------------------------------
     def assemble(self, which, X=None, p=None, q=None):
         """FEM.py:160-183.  which in 'K' | 'M' | 'F'; X = {cell_type: densities} or None."""
@@ -348,6 +412,7 @@ class FEM_Problem(object):
             self.assemble('F')
             self._Kv = self._assemble_values('K', X, p)
             self._K_host = None
+            self._variable_core = False
         elif which == 'F':
             self._assemble_F()
 
@@ -398,7 +463,12 @@ class FEM_Problem(object):
     def solve(self, verbose=True, filtre=0, solve_from_zc=False, h_min=0, modal_solver='lobpcg', sigma=None):
         """FEM.py:189-199.  displacement -> mesh (with mesh.U and point data); modal -> (f[Hz], v[k, ndof])."""
         if solve_from_zc:
-            raise NotImplementedError('variable-core laminate re-assembly (solve_from_zc) is outside the accelerated path')
+            # FEM.py:201-256: the displacement solve re-assembles from `cell_data['zc']` only if K does not exist
+            # yet; the modal solve always re-assembles both matrices
+            if self.physics == 'modal' or self._Kv is None:
+                self.assemble_variable_core('K', h_min)
+            if self.physics == 'modal':
+                self.assemble_variable_core('M', h_min)
         if self.physics == 'displacement':
             return self._displacement_solve(verbose)
         elif self.physics == 'modal':
@@ -454,6 +524,8 @@ class FEM_Problem(object):
 
     def _effective_preconditioner(self):
         p = self.preconditioner
+        if self._variable_core:
+            return 'block_jacobi' if p in ('auto', 'gmg') else p    # per-element matrices: no shared-Ke hierarchy
         if p == 'auto':
             shape = self.structured_grid_shape()
             return 'gmg' if (shape and self.mesh.N_ele >= 64) else 'block_jacobi'

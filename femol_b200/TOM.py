@@ -181,3 +181,33 @@ class SIMP_VIBE(object):
             self.dlmbd = self._dl.cpu().numpy()
             self.mesh.cell_data['X'] = self.X
         return self.mesh
+
+    def density_to_core_height(self):
+        """TOM.py:497-540: map the optimised densities to a core height per element (`cell_data['zc']`), the input
+        of `FEM_Problem.solve(solve_from_zc=True)`.  The bending stiffness of the two shifted laminates is sampled
+        at 100 core heights, normalised to [0, 1], its p-th root taken as the density-height law and inverted by
+        linear interpolation.  Host-side post-processing (100 small laminates), as in the reference."""
+        from .laminate import Layup
+        lb, lc = self.FEM.layups[0], self.FEM.layups[1]
+        hc = -lb.zc - lb.hA / 2 + lc.zc - lc.hA / 2
+        h_values = np.linspace(0, hc, 100)
+        D1, D2 = [], []
+        for hi in h_values:
+            b = Layup(plies=lb.angles, material=lb.mtr, symetric=False, z_core=-hi / 2 - lb.hA / 2)
+            c = Layup(plies=lc.angles, material=lc.mtr, symetric=False, z_core=hi / 2 + lc.hA / 2)
+            D1.append(b.D_mat[0, 0] + c.D_mat[0, 0])
+            D2.append(b.D_mat[1, 1] + c.D_mat[1, 1])
+        base = Layup(plies=lb.angles, material=lb.mtr, symetric=False)
+        Db1, Db2 = base.D_mat[0, 0], base.D_mat[1, 1]
+        X1 = (np.array(D1) - Db1) / (D1[-1] - Db1)
+        X2 = (np.array(D2) - Db2) / (D2[-1] - Db2)
+        X_interp = np.mean([X1, X2], axis=0) ** (1 / self.p)
+        X_interp = np.append(np.append(0, X_interp), 1)
+        h_values = np.append(np.append(0, h_values), hc)
+        zcore = {}
+        for key in self.mesh.cell_data['X']:
+            z = np.interp(self.mesh.cell_data['X'][key], X_interp, h_values)   # scipy interp1d (linear) in the reference
+            z[z < 0] = np.min(h_values)
+            zcore[key] = z
+        self.mesh.cell_data['zc'] = zcore
+        return self.mesh

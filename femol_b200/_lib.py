@@ -26,6 +26,7 @@ SIGNATURES = {
     'femol_device_count': (c_int, []),
     'femol_launch_count': (c_i64, [c_int]),
     'femol_ke_batch': (c_int, [c_int, c_int, c_i64, P, P, P, P, P]),
+    'femol_ke_batch_var': (c_int, [c_int, c_int, c_i64, P, P, P, c_int, P, P]),
     'femol_me_batch': (c_int, [c_int, c_int, c_i64, P, P, P, P, P]),
     'femol_plan_create': (c_int, [c_i64, c_int, c_int, c_i64, P, P, ctypes.POINTER(c_vp)]),
     'femol_plan_destroy': (c_int, [P]),

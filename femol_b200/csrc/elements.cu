@@ -161,34 +161,37 @@ constexpr int KE_WARPS = 4;
 template <int ET, int ND>
 __global__ void __launch_bounds__(KE_WARPS * 32)
 ke_batch_kernel(int64_t n_elem, const double* __restrict__ xy, const int32_t* __restrict__ conn,
-                const double* __restrict__ tens, double* __restrict__ out) {
+                const double* __restrict__ tens, double* __restrict__ out, int tens_stride, int accumulate) {
     constexpr int NN = ElemTraits<ET>::NN;
     constexpr int S = NN * ND;
     constexpr int NR = ND == 2 ? 3 : 8;
     constexpr int NE = (S * S + 31) / 32;
-    __shared__ double sC[NR * NR];
+    // tens_stride = 0: one constitutive block for the whole batch (sCw[0]); 31: one per element, filled by its warp
+    __shared__ double sCw[KE_WARPS][NR * NR];
     __shared__ double sB[KE_WARPS][NR * S];
     __shared__ double sCB[KE_WARPS][NR * S];
     __shared__ double sG[KE_WARPS][3][8];  // dN/dx, dN/dy, N at the current point
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
     // constitutive block tensor: plane = A; plate = A + Bc + D (rows 0-5) and G (rows 6-7)
-    for (int i = threadIdx.x; i < NR * NR; i += blockDim.x) {
+    auto block_entry = [](const double* __restrict__ t, int i) {
         const int r = i / NR, c = i % NR;
         double v = 0.0;
         if (ND == 2) {
-            v = tens[r * 3 + c];
+            v = t[r * 3 + c];
         } else {
-            if (r < 3 && c < 3) v = tens[r * 3 + c];                          // A
-            else if (r >= 3 && r < 6 && c >= 3 && c < 6) v = tens[9 + (r - 3) * 3 + (c - 3)];  // D
-            else if (r >= 6 && c >= 6) v = tens[18 + (r - 6) * 2 + (c - 6)];  // G
+            if (r < 3 && c < 3) v = t[r * 3 + c];                          // A
+            else if (r >= 3 && r < 6 && c >= 3 && c < 6) v = t[9 + (r - 3) * 3 + (c - 3)];  // D
+            else if (r >= 6 && c >= 6) v = t[18 + (r - 6) * 2 + (c - 6)];  // G
             // membrane-bending coupling B (elements.py:1038-1039); the reference's T6 plate ignores it
             // (elements.py:587-621)
-            else if (ET != FEMOL_T6 && r < 3 && c >= 3 && c < 6) v = tens[22 + r * 3 + (c - 3)];
-            else if (ET != FEMOL_T6 && r >= 3 && r < 6 && c < 3) v = tens[22 + (r - 3) * 3 + c];
+            else if (ET != FEMOL_T6 && r < 3 && c >= 3 && c < 6) v = t[22 + r * 3 + (c - 3)];
+            else if (ET != FEMOL_T6 && r >= 3 && r < 6 && c < 3) v = t[22 + (r - 3) * 3 + c];
         }
-        sC[i] = v;
-    }
+        return v;
+    };
+    if (tens_stride == 0)
+        for (int i = threadIdx.x; i < NR * NR; i += blockDim.x) sCw[0][i] = block_entry(tens, i);
     __syncthreads();
 
     const int64_t warp0 = (int64_t)blockIdx.x * KE_WARPS + wid;
@@ -204,6 +207,13 @@ ke_batch_kernel(int64_t n_elem, const double* __restrict__ xy, const int32_t* __
         double acc[NE];
 #pragma unroll
         for (int m = 0; m < NE; ++m) acc[m] = 0.0;
+        const double* sC = sCw[0];
+        if (tens_stride) {   // this element's own tensors (variable-core laminates, FEM.py:697-731)
+            __syncwarp();
+            for (int i = lane; i < NR * NR; i += 32) sCw[wid][i] = block_entry(tens + e * tens_stride, i);
+            __syncwarp();
+            sC = sCw[wid];
+        }
 
         for (int g = 0; g < Rule<ET, ND>::N; ++g) {
             const QPoint q = Rule<ET, ND>::get(g);
@@ -263,7 +273,7 @@ ke_batch_kernel(int64_t n_elem, const double* __restrict__ xy, const int32_t* __
                     const int r = idx / S, c = idx % S;
                     if (r == c && (r % 6) == 5) v = 1.0;
                 }
-                o[idx] = v;
+                o[idx] = accumulate ? o[idx] + v : v;
             }
         }
     }
@@ -427,12 +437,12 @@ me_batch_kernel(int64_t n_elem, const double* __restrict__ xy, const int32_t* __
 
 template <int ET, int ND>
 int launch_ke(int64_t n_elem, const double* xy, const int32_t* conn, const double* tens, double* out,
-              cudaStream_t st) {
+              cudaStream_t st, int tens_stride = 0, int accumulate = 0) {
     int64_t blocks = (n_elem + KE_WARPS - 1) / KE_WARPS;
     const int64_t cap = (int64_t)femol_sm_count() * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    ke_batch_kernel<ET, ND><<<(int)blocks, KE_WARPS * 32, 0, st>>>(n_elem, xy, conn, tens, out);
+    ke_batch_kernel<ET, ND><<<(int)blocks, KE_WARPS * 32, 0, st>>>(n_elem, xy, conn, tens, out, tens_stride, accumulate);
     FEMOL_LAUNCH_CHECK();
     return FEMOL_OK;
 }
@@ -470,6 +480,31 @@ extern "C" int femol_ke_batch(int etype, int ndof, int64_t n_elem, const double*
     }
 #undef KE_CASE
     femol_set_error("femol_ke_batch: unknown element type %d", etype);
+    return FEMOL_E_ARG;
+}
+
+// Ke with ONE TENSOR SET PER ELEMENT (tensors [n_elem][31]); accumulate != 0 adds to ke_out (the drilling diagonal, which
+// is SET to 1 per call, adds up like in the reference's Ke_base + Ke_coat, FEM.py:728)
+extern "C" int femol_ke_batch_var(int etype, int ndof, int64_t n_elem, const double* xy, const int32_t* conn,
+                                  const double* tensors, int accumulate, double* ke_out, void* stream) {
+    FEMOL_REQUIRE(n_elem >= 0 && xy && conn && tensors && ke_out, "femol_ke_batch_var: null argument");
+    FEMOL_REQUIRE(ndof == 2 || ndof == 6, "femol_ke_batch_var: ndof must be 2 (plane) or 6 (plate)");
+    if (n_elem == 0) return FEMOL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define KEV_CASE(ET)                                                                                   \
+    case ET:                                                                                           \
+        return ndof == 2 ? launch_ke<ET, 2>(n_elem, xy, conn, tensors, ke_out, st, 31, accumulate)      \
+                         : launch_ke<ET, 6>(n_elem, xy, conn, tensors, ke_out, st, 31, accumulate);
+    switch (etype) {
+        case FEMOL_T3:
+            FEMOL_REQUIRE(ndof == 2, "femol_ke_batch_var: T3 supports plane stress only (reference elements.py:231)");
+            return launch_ke<FEMOL_T3, 2>(n_elem, xy, conn, tensors, ke_out, st, 31, accumulate);
+        KEV_CASE(FEMOL_Q4)
+        KEV_CASE(FEMOL_T6)
+        KEV_CASE(FEMOL_Q8)
+    }
+#undef KEV_CASE
+    femol_set_error("femol_ke_batch_var: unknown element type %d", etype);
     return FEMOL_E_ARG;
 }
 

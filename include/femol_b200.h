@@ -64,6 +64,13 @@ int64_t femol_launch_count(int reset);
  * out: [n_elem][size][size], size = nn*ndof. */
 int femol_ke_batch(int etype, int ndof, int64_t n_elem, const double* xy, const int32_t* conn,
                    const double* tensors, double* ke_out, void* stream);
+
+/* Element stiffness matrices with one tensor set PER ELEMENT: the variable-core laminate re-assembly of
+ * FEM_Problem._K_variable_core_laminate_data (FEM.py:697-731, `solve(solve_from_zc=True)`).  tensors [n_elem][31] in
+ * the layout of femol_ke_batch.  accumulate != 0: ke_out += Ke (base laminate first, coating laminate second; the
+ * drilling diagonal is SET to 1 per call, so it adds up to 2 exactly as in the reference's Ke_base + Ke_coat). */
+int femol_ke_batch_var(int etype, int ndof, int64_t n_elem, const double* xy, const int32_t* conn,
+                       const double* tensors, int accumulate, double* ke_out, void* stream);
 int femol_me_batch(int etype, int ndof, int64_t n_elem, const double* xy, const int32_t* conn,
                    const double* V, double* me_out, void* stream);
 

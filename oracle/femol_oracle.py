@@ -982,6 +982,48 @@ def global_matrices(arr, which='K', X=None, p=None):
     return assemble_csr(rows, cols, data, ntot)
 
 
+def variable_core_matrices(case, zc, h_min=0.0, which='K', jitter_fn=None):
+    """K / M of a two-laminate plate whose core height varies per element (FEM.py:697-731, 873-896, used by
+    `solve(solve_from_zc=True)`): for zc > h_min the element is Ke(base laminate shifted to -h/2 + hA0/2) +
+    Ke(coating laminate shifted to +h/2 - hA1/2) with h = zc + hA0 + hA1, each with the FULL ply list and
+    symetric=False; otherwise the unshifted base laminate alone.  Mass: Me(base) (+ Me(coat) if zc > h_min)."""
+    arr = case_arrays(case, jitter_fn)
+    pts, cells, ndof, et = arr['points'], arr['cells'], arr['ndof'], arr['etype']
+    xy = pts[cells][:, :, :2]
+    par = [MATERIAL_LIB[m[1]] for m in case['materials']]
+    angles, hA = [], []
+    for t, pr in zip(case['tensors'], par):
+        _, plies, sym, _, _ = t
+        full = np.hstack([np.array(plies), np.flip(np.array(plies))]) if sym else np.array(plies)
+        angles.append(full); hA.append(full.shape[0] * pr['ho'])
+
+    def lam(k, z_core):
+        pr = par[k]
+        return layup_tensors(pr['Ex'], pr['Ey'], pr['Es'], pr['vx'], pr['ho'], angles[k], False, z_core, 0,
+                             pr.get('Gyz'), pr.get('Gxz'))[0]
+
+    size = xy.shape[1] * ndof
+    E = np.zeros((cells.shape[0], size, size))
+    if which == 'M':
+        Mb = me_batch(et, xy, ndof, arr['rho'][0], arr['ho'][0])
+        Mc = me_batch(et, xy, ndof, arr['rho'][1], arr['ho'][1])
+    for e in range(cells.shape[0]):
+        above = zc[e] > h_min
+        if which == 'K':
+            if above:
+                h = zc[e] + hA[0] + hA[1]
+                E[e] = ke_batch(et, xy[e:e + 1], ndof, lam(0, -h / 2 + hA[0] / 2))[0] + \
+                    ke_batch(et, xy[e:e + 1], ndof, lam(1, h / 2 - hA[1] / 2))[0]
+            else:
+                E[e] = ke_batch(et, xy[e:e + 1], ndof, lam(0, 0))[0]
+        else:
+            E[e] = Mb[e] + (Mc[e] if above else 0.0)
+    rows, cols = coo_pattern(cells, ndof)
+    ntot = ndof * pts.shape[0]
+    data = apply_bc_data(E.reshape(-1), rows, cols, arr['fixed_idx'], ntot)
+    return assemble_csr(rows, cols, data, ntot), arr
+
+
 class VibeProblem(object):
     """SIMP_VIBE on plain arrays (TOM.py:37-132, 374-386) with the dense modal solve (FEM.py:277)."""
 

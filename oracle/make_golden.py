@@ -211,6 +211,35 @@ def gen_stress():
     return out
 
 
+VARCORE_CASE = dict(cases.CASES['modal_q4_plate_coat_6x6'], mesh=('Q4J', 1., 1., 6, 6, 0.15))
+VARCORE_STATIC = dict(VARCORE_CASE, physics='displacement',
+                      forces=[([0, 0, -5.0, 0, 0, 0], ([1.], [[0, 1.]]))])
+
+
+def gen_variable_core():
+    """`solve(solve_from_zc=True, h_min)` of the reference (FEM.py:201-256, 697-731, 873-896): per-element core
+    heights on a jittered two-laminate plate; K, M, the static solution and the modal spectrum."""
+    out = {}
+    h_min = 0.003
+    problem = cases.build_problem(FEMOL, VARCORE_CASE)
+    zc = np.random.default_rng(5).uniform(0.0, 0.012, problem.mesh.N_ele)
+    problem.mesh.cell_data['zc'] = {'quad': zc}
+    w, v = quiet(problem.solve, verbose=False, filtre=0, solve_from_zc=True, h_min=h_min, modal_solver='fast')
+    out.update(csr_parts('K', problem.K)); out.update(csr_parts('M', problem.M))
+    out['w'] = np.asarray(w); out['zc'] = zc; out['h_min'] = np.array(h_min)
+    static = cases.build_problem(FEMOL, VARCORE_STATIC)
+    static.mesh.cell_data['zc'] = {'quad': zc}
+    mesh = quiet(static.solve, verbose=False, solve_from_zc=True, h_min=h_min)
+    out['U'] = mesh.U.copy(); out['F'] = static.F.copy()
+    # SIMP_VIBE.density_to_core_height (TOM.py:497-540) on a seeded density field
+    vibe = FEMOL.SIMP_VIBE(cases.build_problem(FEMOL, VARCORE_CASE), volfrac=0.5, p=3, q=1, rmin=1.5)
+    X = cases.density_field(vibe.mesh.N_ele, seed=9)
+    vibe.mesh.cell_data['X'] = {'quad': X}
+    m2 = vibe.density_to_core_height()
+    out['X_dens'] = X; out['zc_from_density'] = np.asarray(m2.cell_data['zc']['quad'])
+    np.savez_compressed(os.path.join(GOLD, 'variable_core.npz'), **out)
+
+
 def gen_modal_filters():
     """The eigen-filters of the reference (FEM.py:335-418) applied to synthetic spectra."""
     rng = np.random.default_rng(11)
@@ -233,10 +262,12 @@ def gen_modal_filters():
 
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
-    todo = sys.argv[1:] or (['elements', 'stress', 'modal_filters'] + list(cases.CASES))
+    todo = sys.argv[1:] or (['elements', 'stress', 'modal_filters', 'variable_core'] + list(cases.CASES))
     for name in todo:
         if name == 'stress':
             gen_stress()
+        elif name == 'variable_core':
+            gen_variable_core()
         elif name == 'modal_filters':
             gen_modal_filters()
         elif name == 'elements':

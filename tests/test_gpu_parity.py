@@ -896,3 +896,43 @@ def test_fast_galerkin_coarsening_matches_generic(F, monkeypatch, nx, ny, model)
         assert out[old][1]['converged']
     assert abs(out['0'][1]['iterations'] - out['1'][1]['iterations']) <= 1, (out['0'][1], out['1'][1])
     assert rel(out['0'][0], out['1'][0]) < 1e-6
+
+
+def test_variable_core_laminate_solves(F, golden):
+    """`solve(solve_from_zc=True, h_min)` (FEM.py:201-256, 697-731, 873-896): K and M of per-element shifted laminates
+    against the reference's matrices, the static solution against its `spsolve`, the lowest modes against the dense
+    eigen-solve of the same pencil."""
+    import scipy.linalg
+    g = golden('variable_core')
+    case = dict(cases.CASES['modal_q4_plate_coat_6x6'], mesh=('Q4J', 1., 1., 6, 6, 0.15))
+    h_min = float(g['h_min'])
+    p = cases.build_problem(F, case)
+    p.mesh.cell_data['zc'] = {'quad': g['zc']}
+    p.n_modes = 4
+    p.modal_tol = 1e-8
+    w, v = p.solve(verbose=False, solve_from_zc=True, h_min=h_min)
+    for which, A in (('K', p.K), ('M', p.M)):
+        assert np.array_equal(A.indptr, g[which + '_indptr']) and np.array_equal(A.indices, g[which + '_indices'])
+        assert rel(A.data, g[which + '_data']) < 1e-12, which
+    keep = np.ones(p.K.shape[0], bool)
+    keep[p.fixed_dofs()] = False
+    keep[5::6] = False
+    lam = scipy.linalg.eigh(p.K[keep][:, keep].toarray(), p.M[keep][:, keep].toarray(), eigvals_only=True, subset_by_index=[0, 3])
+    assert np.allclose(np.sort(w)[:4], np.sqrt(lam) / (2 * np.pi), rtol=1e-6), (w, np.sqrt(lam) / (2 * np.pi))
+    for fi in np.sort(w)[:4]:                       # and they are in the spectrum the reference returned
+        assert np.min(np.abs(g['w'] - fi) / fi) < 1e-4
+    # static: same K (assembled from zc because none exists yet), the reference's load
+    case_s = dict(case, physics='displacement', forces=[([0, 0, -5.0, 0, 0, 0], ([1.], [[0, 1.]]))])
+    ps = cases.build_problem(F, case_s)
+    ps.mesh.cell_data['zc'] = {'quad': g['zc']}
+    ps.solver_rtol = 1e-11
+    U = ps.solve(verbose=False, solve_from_zc=True, h_min=h_min).U
+    assert ps.solver_info['preconditioner'] == 'block_jacobi'
+    assert rel(ps.K.data, g['K_data']) < 1e-12
+    r = np.linalg.norm(ps.K @ g['U'] - ps.F) / np.linalg.norm(ps.F)          # the reference's own residual level
+    assert np.linalg.norm(ps.K @ U - ps.F) / np.linalg.norm(ps.F) < max(1e-8, 10 * r)
+    assert rel(U, g['U']) < 1e-5
+    # density -> core height through the mirror class
+    vibe = F.SIMP_VIBE(cases.build_problem(F, case), volfrac=0.5, p=3, q=1, rmin=1.5)
+    vibe.mesh.cell_data['X'] = {'quad': g['X_dens']}
+    assert np.allclose(vibe.density_to_core_height().cell_data['zc']['quad'], g['zc_from_density'], rtol=1e-13, atol=0)

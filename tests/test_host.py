@@ -178,3 +178,34 @@ def test_modal_filters_match_reference(golden):
     plane = F.FEM_Problem('modal', 'plane', mesh)
     with pytest.raises(TypeError):                      # the reference's mesh-mode filter returns None for plane models
         plane._filter_eigenvalues_1(g['w'].copy(), g['v'][:, :18].copy())
+
+
+def test_variable_core_host_pieces(golden):
+    """Host side of the variable-core laminate path: the vectorised per-element tensors (shift formulas) against
+    the oracle's per-element laminates, and SIMP_VIBE.density_to_core_height (TOM.py:497-540) against the reference."""
+    import types
+    import femol_b200 as F
+    from femol_b200.elements import pack_tensors
+    g = golden('variable_core')
+    case = dict(cases.CASES['modal_q4_plate_coat_6x6'], mesh=('Q4J', 1., 1., 6, 6, 0.15))
+    p = cases.build_problem(F, case)
+    zc, h_min = g['zc'], float(g['h_min'])
+    Tb, Tc, above = p._variable_core_tensors(zc, h_min)
+    par = [o.MATERIAL_LIB['general_flax'], o.MATERIAL_LIB['general_carbon']]
+    lb, lc = p.layups
+
+    def lam(k, lay, z):
+        q = par[k]
+        return pack_tensors(o.layup_tensors(q['Ex'], q['Ey'], q['Es'], q['vx'], q['ho'], lay.angles, False, z, 0,
+                                            q.get('Gyz'), q.get('Gxz'))[0])
+    for e in range(zc.shape[0]):
+        h = zc[e] + lb.hA + lc.hA
+        if above[e]:
+            assert np.allclose(Tb[e], lam(0, lb, -h / 2 + lb.hA / 2), rtol=1e-12, atol=1e-12 * np.abs(Tb[e]).max())
+            assert np.allclose(Tc[e], lam(1, lc, h / 2 - lc.hA / 2), rtol=1e-12, atol=1e-12 * np.abs(Tc[e]).max())
+        else:
+            assert np.allclose(Tb[e], lam(0, lb, 0.0), rtol=1e-12, atol=1e-12 * np.abs(Tb[e]).max()) and not Tc[e].any()
+    p.mesh.cell_data['X'] = {'quad': g['X_dens']}
+    fake = types.SimpleNamespace(FEM=p, mesh=p.mesh, p=3)
+    mesh = F.SIMP_VIBE.density_to_core_height(fake)
+    assert np.allclose(mesh.cell_data['zc']['quad'], g['zc_from_density'], rtol=1e-13, atol=0)
