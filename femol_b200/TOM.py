@@ -45,6 +45,7 @@ class SIMP_VIBE(object):
         self.dlmbd = 0
         self.loop = 0
         self.change = None
+        self.save_root = 'Results/_topopt_cache/' if saving_root is None else saving_root   # TOM.py:84-86
         self.archive = True
         d = self.FEM.device
         self._x = torch.full((d.n_elem,), float(volfrac), dtype=torch.float64, device=d.dev)
@@ -153,7 +154,9 @@ class SIMP_VIBE(object):
 
     def solve(self, v_ref, converge=0.01, min_iter=1, max_iter=100, plot=True, save=True, verbose=True,
               convergence_criteria='change', mesh_filename=None, eigvals_filename=None, eigvecs_filename=None):
-        """TOM.py:87-132 (`plot` / `save` ignored: matplotlib / meshio are outside the accelerated path)."""
+        """TOM.py:87-132.  `plot` (matplotlib) is ignored.  `save`: the reference rewrites the same result files on
+        every iteration (TOM.py:134-152); they are written once, after the last iteration."""
+        files = self._get_saving_filenames(mesh_filename, eigvals_filename, eigvecs_filename)
         self.change = 1
         self.loop = 0
         ctype = self.mesh.contains[0]
@@ -180,7 +183,31 @@ class SIMP_VIBE(object):
             self.v = self._v.cpu().numpy()
             self.dlmbd = self._dl.cpu().numpy()
             self.mesh.cell_data['X'] = self.X
+        if save:
+            self.save_TOM_iteration(*files)
         return self.mesh
+
+    def _get_saving_filenames(self, mesh_filename, eigvals_filename, eigvecs_filename):
+        """TOM.py:211-223"""
+        from .utils import unique_time_string
+        stamp = unique_time_string()
+        root = self.save_root
+        return [root + (name if name is not None else base + stamp)
+                for name, base in zip((mesh_filename, eigvals_filename, eigvecs_filename), ('TOM_', 'eigvals_', 'eigvecs_'))]
+
+    def save_TOM_iteration(self, msh_file, eig_file, vec_file):
+        """TOM.py:134-152: core heights (two-laminate problems), penalised densities `X_real`, the mesh as VTK and the
+        tracked eigenvalue history as .npy."""
+        import os
+        if len(self.FEM.layups) == 2:                 # the reference assumes a base + coating laminate here
+            self.mesh = self.density_to_core_height()
+        ctype = self.mesh.contains[0]
+        self.mesh.cell_data['X_real'] = {ctype: np.asarray(self.mesh.cell_data['X'][ctype]) ** self.p}
+        folder = os.path.dirname(msh_file)
+        if folder and not os.path.isdir(folder):
+            os.makedirs(folder, exist_ok=True)
+        self.mesh.save(msh_file)
+        np.save(eig_file, np.array(self.lmbds))
 
     def density_to_core_height(self):
         """TOM.py:497-540: map the optimised densities to a core height per element (`cell_data['zc']`), the input

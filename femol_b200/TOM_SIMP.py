@@ -191,8 +191,9 @@ class SIMP_COMP(object):
         return self.change, self.c
 
     def solve(self, converge=0.01, max_iter=100, plot=True, save=True):
-        """TOM_SIMP.py:34-81.  `plot` / `save` (matplotlib, VTK via meshio) are outside the accelerated path
-        and ignored."""
+        """TOM_SIMP.py:34-81.  `plot` (matplotlib) is ignored.  `save`: the reference rewrites ONE VTK file
+        (named after the start time) on every iteration; the same file is written once, after the last iteration."""
+        start_time = unique_time_string()
         self.change = 1
         self.loop = 0
         ctype = self.mesh.contains[0]
@@ -220,7 +221,14 @@ class SIMP_COMP(object):
             self.dc = self._dc.cpu().numpy()
             self.mesh.cell_data['X'] = self.X
         self.mesh.U = self.U
+        if save:
+            self._save_TOM_result(start_time)
         return self.mesh
 
-    def _save_TOM_result(self, timestring=None):
-        raise NotImplementedError('VTK export (meshio) is outside the accelerated path; see mesh.cell_data')
+    def _save_TOM_result(self, timestring):
+        """TOM_SIMP.py:108-116: Results/_topopt_cache/TOM_<time>.vtk, or the working directory if that folder
+        does not exist."""
+        try:
+            self.mesh.save('Results/_topopt_cache/TOM_' + timestring)
+        except FileNotFoundError:
+            self.mesh.save('TOM_' + unique_time_string())

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import elements
 
-__all__ = ['Mesh', 'rectangle_Q4', 'rectangle_T3', 'rectangle_T6', 'rectangle_Q8']
+__all__ = ['Mesh', 'load_vtk', 'rectangle_Q4', 'rectangle_T3', 'rectangle_T6', 'rectangle_Q8']
 
 
 class Mesh(object):
@@ -50,6 +50,43 @@ class Mesh(object):
         if 'quad' in self.contains and (self.areas['quad'] < 0).any():
             self.fix_quadrilaterals()
             self.areas = self.element_areas()
+
+    # ---- result IO ---------------------------------------------------------------------------------
+    # VTK cell types and the permutation local node -> VTK node (6-node triangles are corner, mid, corner, mid, ...
+    # here, mesh.py:105-138, and corners-then-mids in VTK; 8-node quads are already corners-then-mids)
+    _VTK = {3: (5, [0, 1, 2]), 4: (9, [0, 1, 2, 3]), 6: (22, [0, 2, 4, 1, 3, 5]), 8: (23, list(range(8)))}
+
+    def save(self, file):
+        """mesh.py:242-267 without meshio: `file`.vtk, legacy VTK (binary, big-endian) UNSTRUCTURED_GRID with the
+        points, the cells of every type in `contains`, `point_data` (per-node arrays) and `cell_data`
+        ({name: {cell_type: array}}, concatenated in `contains` order like the reference does)."""
+        cells = [np.asarray(self.cells[c], dtype=np.int64) for c in self.contains]
+        n_cells = sum(c.shape[0] for c in cells)
+        with open(file + '.vtk', 'wb') as f:
+            f.write(b'# vtk DataFile Version 4.2\nfemol_b200 mesh\nBINARY\nDATASET UNSTRUCTURED_GRID\n')
+            f.write(('POINTS %d double\n' % self.points.shape[0]).encode())
+            f.write(np.ascontiguousarray(self.points, dtype='>f8').tobytes()); f.write(b'\n')
+            f.write(('CELLS %d %d\n' % (n_cells, sum(c.shape[0] * (c.shape[1] + 1) for c in cells))).encode())
+            for c in cells:
+                perm = self._VTK[c.shape[1]][1]
+                rec = np.hstack([np.full((c.shape[0], 1), c.shape[1], dtype=np.int64), c[:, perm]])
+                f.write(rec.astype('>i4').tobytes())
+            f.write(('\nCELL_TYPES %d\n' % n_cells).encode())
+            for c in cells:
+                f.write(np.full(c.shape[0], self._VTK[c.shape[1]][0], dtype='>i4').tobytes())
+            f.write(b'\n')
+
+            def scalars(name, arr):
+                f.write(('SCALARS %s double 1\nLOOKUP_TABLE default\n' % str(name).replace(' ', '_')).encode())
+                f.write(np.ascontiguousarray(arr, dtype='>f8').tobytes()); f.write(b'\n')
+            if self.point_data:
+                f.write(('POINT_DATA %d\n' % self.points.shape[0]).encode())
+                for name, arr in self.point_data.items():
+                    scalars(name, np.asarray(arr, dtype=np.float64).reshape(-1))
+            if self.cell_data:
+                f.write(('CELL_DATA %d\n' % n_cells).encode())
+                for name, per_type in self.cell_data.items():
+                    scalars(name, np.concatenate([np.asarray(per_type[c], dtype=np.float64).reshape(-1) for c in self.contains]))
 
     # ---- geometry -------------------------------------------------------------------------------
     @property
@@ -268,3 +305,82 @@ def rectangle_Q8(Lx, Ly, nelx, nely):
     v_id = lambda ii, jj: nc + nelx * (nely + 1) + jj * (nelx + 1) + ii
     cells = np.stack([q[:, 0], q[:, 1], q[:, 2], q[:, 3], h_id(i, j), v_id(i + 1, j), h_id(i, j + 1), v_id(i, j)], 1)
     return Mesh(np.vstack([points, hmid, vmid]), {'quad': cells}, structured=True, quad_element=elements.Q8)
+
+
+def load_vtk(file):
+    """mesh.py:827-844 without meshio: read a legacy-VTK UNSTRUCTURED_GRID (binary as written by `Mesh.save`, or
+    ASCII) with triangle / quad / 6-node triangle / 8-node quad cells back into a Mesh with its point and cell data."""
+    raw = open(file, 'rb').read()
+    pos = 0
+
+    def line():
+        nonlocal pos
+        while True:
+            end = raw.index(b'\n', pos)
+            out = raw[pos:end].decode().strip()
+            pos = end + 1
+            if out:
+                return out
+    line(); line()
+    binary = line().upper() == 'BINARY'
+    assert line().upper().endswith('UNSTRUCTURED_GRID'), 'only UNSTRUCTURED_GRID files are supported'
+
+    def numbers(count, dtype):
+        nonlocal pos
+        if binary:
+            out = np.frombuffer(raw, dtype=dtype, count=count, offset=pos)
+            pos += count * np.dtype(dtype).itemsize
+            return out.astype(np.float64 if 'f' in dtype else np.int64)
+        vals = []
+        while len(vals) < count:
+            vals += line().split()
+        return np.array(vals[:count], dtype=np.float64 if 'f' in dtype else np.int64)
+    points = cells_flat = types = None
+    point_data, cell_data_flat = {}, {}
+    target = None
+    n_points = n_cells = 0
+    while pos < len(raw):
+        try:
+            head = line().split()
+        except ValueError:
+            break
+        key = head[0].upper()
+        if key == 'POINTS':
+            n_points = int(head[1])
+            points = numbers(3 * n_points, '>f8' if head[2] == 'double' else '>f4').reshape(-1, 3)
+        elif key == 'CELLS':
+            n_cells = int(head[1])
+            cells_flat = numbers(int(head[2]), '>i4')
+        elif key == 'CELL_TYPES':
+            types = numbers(int(head[1]), '>i4')
+        elif key == 'POINT_DATA':
+            target = (point_data, n_points)
+        elif key == 'CELL_DATA':
+            target = (cell_data_flat, n_cells)
+        elif key == 'SCALARS':
+            line()                                   # LOOKUP_TABLE default
+            target[0][head[1]] = numbers(target[1], '>f8' if head[2] == 'double' else '>f4')
+    inverse = {code: (n, np.argsort(perm)) for n, (code, perm) in Mesh._VTK.items()}
+    per_type, order = {}, []
+    o = 0
+    for t in types:
+        n, inv = inverse[int(t)]
+        nodes = cells_flat[o + 1:o + 1 + n][inv]
+        o += n + 1
+        key = 'quad' if n in (4, 8) else 'triangle'
+        if key not in per_type:
+            per_type[key] = []
+            order.append(key)
+        per_type[key].append(nodes)
+    cell_dict = {k: np.array(per_type[k], dtype=np.int64) for k in order}
+    kw = {}
+    if 'triangle' in cell_dict and cell_dict['triangle'].shape[1] == 6:
+        kw['tri_element'] = elements.T6
+    if 'quad' in cell_dict and cell_dict['quad'].shape[1] == 8:
+        kw['quad_element'] = elements.Q8
+    mesh = Mesh(points, cell_dict, **kw)
+    mesh.point_data = point_data
+    bounds = np.cumsum([0] + [cell_dict[k].shape[0] for k in mesh.contains])
+    mesh.cell_data = {name: {k: arr[bounds[i]:bounds[i + 1]] for i, k in enumerate(mesh.contains)}
+                      for name, arr in cell_data_flat.items()}
+    return mesh

@@ -936,3 +936,26 @@ def test_variable_core_laminate_solves(F, golden):
     vibe = F.SIMP_VIBE(cases.build_problem(F, case), volfrac=0.5, p=3, q=1, rmin=1.5)
     vibe.mesh.cell_data['X'] = {'quad': g['X_dens']}
     assert np.allclose(vibe.density_to_core_height().cell_data['zc']['quad'], g['zc_from_density'], rtol=1e-13, atol=0)
+
+
+def test_result_files(F, golden, tmp_path, monkeypatch):
+    """`save=True` of the optimisers (TOM_SIMP.py:108-116, TOM.py:134-152): the VTK result written through Mesh.save is
+    read back by load_vtk with the final densities; SIMP_VIBE also stores the tracked eigenvalue history."""
+    import glob
+    from femol_b200.mesh import load_vtk
+    monkeypatch.chdir(tmp_path)
+    problem = cases.build_problem(F, cases.CASES['comp_q4_30x15'])
+    opt = F.SIMP_COMP(problem, volfrac=0.4, penal=3, rmin=1.5)
+    mesh = opt.solve(converge=0.0, max_iter=2, plot=False, save=True)
+    files = glob.glob(str(tmp_path / 'TOM_*.vtk'))
+    assert len(files) == 1
+    back = load_vtk(files[0])
+    assert np.array_equal(back.cell_data['X']['quad'], mesh.cell_data['X']['quad'])
+    assert np.array_equal(back.point_data['d2_Ux'], mesh.point_data['d2_Ux'])
+    case, g = cases.CASES['vibe_q4_plate_10x10'], golden('vibe_q4_plate_10x10')
+    vibe = F.SIMP_VIBE(cases.build_problem(F, case), volfrac=0.5, p=3, q=1, rmin=1.5, saving_root=str(tmp_path) + '/vibe_')
+    m2 = vibe.solve(g['v_ref'], converge=0.0, min_iter=1, max_iter=2, plot=False, save=True, verbose=False,
+                    mesh_filename='mesh', eigvals_filename='eigs')
+    back = load_vtk(str(tmp_path / 'vibe_mesh.vtk'))
+    assert np.allclose(back.cell_data['X_real']['quad'], m2.cell_data['X']['quad'] ** 3, rtol=1e-15)
+    assert np.array_equal(np.load(str(tmp_path / 'vibe_eigs.npy')), np.array(vibe.lmbds))

@@ -209,3 +209,29 @@ def test_variable_core_host_pieces(golden):
     fake = types.SimpleNamespace(FEM=p, mesh=p.mesh, p=3)
     mesh = F.SIMP_VIBE.density_to_core_height(fake)
     assert np.allclose(mesh.cell_data['zc']['quad'], g['zc_from_density'], rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize('kind', ['Q4', 'T3', 'T6'])
+def test_vtk_round_trip(tmp_path, kind):
+    """Mesh.save / load_vtk (mesh.py:242-267, 827-844, without meshio): points, cells (6-node triangles through the
+    VTK node order and back), point data and cell data survive a round trip; the file is a legacy-VTK grid."""
+    import femol_b200 as F
+    from femol_b200.mesh import load_vtk
+    mesh = {'Q4': F.mesh.rectangle_Q4, 'T3': F.mesh.rectangle_T3, 'T6': F.mesh.rectangle_T6}[kind](3., 2., 3, 2)
+    rng = np.random.default_rng(0)
+    ctype = mesh.contains[0]
+    mesh.add_displacement(rng.standard_normal(2 * mesh.N_nodes), 2)
+    mesh.cell_data['X'] = {ctype: rng.uniform(0, 1, mesh.N_ele)}
+    mesh.cell_data['zc'] = {ctype: rng.uniform(0, 1, mesh.N_ele)}
+    path = str(tmp_path / 'result')
+    mesh.save(path)
+    head = open(path + '.vtk', 'rb').read(80)
+    assert head.startswith(b'# vtk DataFile Version') and b'BINARY' in head
+    back = load_vtk(path + '.vtk')
+    assert np.array_equal(back.points, mesh.points)
+    assert np.array_equal(np.asarray(back.cells[ctype]), np.asarray(mesh.cells[ctype]))
+    assert back.ElementClasses[ctype] is mesh.ElementClasses[ctype]
+    for k in ('Ux', 'Uy'):
+        assert np.array_equal(back.point_data[k], mesh.point_data[k])
+    for k in ('X', 'zc'):
+        assert np.array_equal(back.cell_data[k][ctype], mesh.cell_data[k][ctype])
