@@ -49,7 +49,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // straight-line (no loop around the multiply), so the element-matrix operands are read from the constant bank
 // where they are used instead of being hoisted into, and spilled from, registers.
 template <int ND, bool COAT, int TI, int TJ, int NT, int NPT, int MODE>
-__global__ void __launch_bounds__(TI * TJ / NPT, ND == 2 ? 3 : (COAT ? 1 : 2))
+__global__ void __launch_bounds__(TI * TJ / NPT, ND == 2 ? (COAT ? 2 : 3) : (COAT ? 1 : 2))
 stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int ny, int tiles_i, int n_tiles, int cta0,
                     const double* __restrict__ xpow, const uint8_t* __restrict__ fixed,
                     const double* __restrict__ u, double* __restrict__ y, const double* __restrict__ dot_with,
