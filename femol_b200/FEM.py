@@ -130,6 +130,13 @@ class FEM_Problem(object):
         self.preconditioner = 'auto'
         self.gmg_smoothing_steps = 1     # pre = post sweeps of damped block-Jacobi (tuned on cfg 2, tools/tune_gmg.py)
         self.gmg_omega = 0.7
+        # Q4 Mindlin plates: second multigrid cycle on the sign-modulated operator S K S, which removes the hourglass
+        # family of the selectively integrated element from the CG spectrum (femol_gmg_attach_modulated).  'auto': plate
+        # models whose boundary is not fully supported in w (with all edges supported the family is restrained) and
+        # whose thickness is at least 8 element sizes: the cycle costs as much as the first one and, measured on a
+        # cantilever (n = 200): t/h = 20: 262 -> 67 iterations, 10: 270 -> 119, 4: 386 -> 279, 2: 540 -> 558,
+        # 0.5: 2264 -> 2978; far below one element size it can even prevent convergence
+        self.gmg_hourglass = 'auto'
         self.warm_start = True
         # structured rectangle_Q4 grids: PCG / multigrid apply K matrix-free (csrc/stencil.cu); K itself is
         # still assembled (it is what .K returns and what the block eigen-solver multiplies with)
@@ -155,12 +162,16 @@ class FEM_Problem(object):
         self._X_modal = None  # last eigenvector block (warm start)
         self._mask_key = None
         self._mask_dev = None
+        self._mask_host = None
         self._fixed_dofs = None
         self._fixed_dofs_key = None
         self._F_key = None
         self._F_ref = None
         self._grid_shape = None
         self._gmg = None
+        self._gmg2 = None           # hierarchy of S K S (plates), on a view of the plan
+        self._plan_view = None
+        self._gmg2_refs = None
         self._gmg_mask_key = None
         self._gmg_stale = True
         self._gmg_ws = None
@@ -170,9 +181,7 @@ class FEM_Problem(object):
 
     def __del__(self):
         try:
-            if getattr(self, '_gmg', None) is not None:
-                _lib.load().femol_gmg_destroy(self._gmg)
-                self._gmg = None
+            self._destroy_gmg()
         except Exception:
             pass
 
@@ -270,6 +279,7 @@ class FEM_Problem(object):
                 mask[nodes] |= bits
             self.fixed_nodes = np.concatenate(nodes_all) if nodes_all else np.array([])
             self._mask_dev = torch.from_numpy(mask).to(self.device.dev) if self.fixed_ddls else None
+            self._mask_host = mask
             self._mask_key = key
         return self._mask_dev
 
@@ -537,21 +547,71 @@ class FEM_Problem(object):
         """Create (once per Dirichlet set) and refresh (once per assembled K) the multigrid hierarchy."""
         d = self.device
         mask = self._fixed_mask()
-        if self._gmg is None or self._gmg_mask_key != self._mask_key:
-            if self._gmg is not None:
-                _lib.load().femol_gmg_destroy(self._gmg)
+        hourglass = self._hourglass_enabled()
+        if self._gmg is None or self._gmg_mask_key != self._mask_key or hourglass != (self._gmg2 is not None):
+            self._destroy_gmg()
             nx, ny = self.structured_grid_shape()
             handle = ctypes.c_void_p()
             _lib.call('femol_gmg_create', nx, ny, self.N_dof, d.plan, _lib.ptr(mask), int(self.gmg_smoothing_steps),
                       float(self.gmg_omega), _lib.stream(), ctypes.byref(handle))
             self._gmg, self._gmg_mask_key, self._gmg_stale = handle, self._mask_key, True
+            if hourglass:
+                view, h2 = ctypes.c_void_p(), ctypes.c_void_p()
+                _lib.call('femol_plan_create_view', d.plan, ctypes.byref(view))
+                self._plan_view = view
+                _lib.call('femol_gmg_create', nx, ny, self.N_dof, view, _lib.ptr(mask), int(self.gmg_smoothing_steps),
+                          float(self.gmg_omega), _lib.stream(), ctypes.byref(h2))
+                self._gmg2 = h2
+                _lib.call('femol_gmg_attach_modulated', self._gmg, h2)
         if self._gmg_stale:
             Eb, _ = self._element_matrices('K', False)
             Ec = self._element_matrices('K', True)[0] if self.coating else None
-            _lib.call('femol_gmg_setup', self._gmg, _lib.ptr(Eb), _lib.ptr(Ec),
-                      _lib.ptr(d.xpow) if self._K_scaled else None, _lib.ptr(self._Kv), _lib.stream())
+            xp = _lib.ptr(d.xpow) if self._K_scaled else None
+            _lib.call('femol_gmg_setup', self._gmg, _lib.ptr(Eb), _lib.ptr(Ec), xp, _lib.ptr(self._Kv), _lib.stream())
+            if self._gmg2 is not None:
+                # S_e Ke S_e with S_e = (+, -, +, -) over the element's nodes (Q4 order (0,0) (1,0) (1,1) (0,1)); the
+                # view's matrix-free descriptor is tagged with K's value array: level 0 of the second hierarchy is
+                # applied matrix-free, and its block-diagonal inverse is that of K (S is constant within a node)
+                sgn = torch.tensor([1.0, -1.0, 1.0, -1.0], dtype=torch.float64, device=d.dev).repeat_interleave(self.N_dof)
+                flip = sgn[:, None] * sgn[None, :]
+                Ebh = (Eb[:1] * flip).contiguous()
+                Ech = (Ec[:1] * flip).contiguous() if Ec is not None else None
+                hb = np.ascontiguousarray(Ebh[0].cpu().numpy().reshape(-1))
+                hc = np.ascontiguousarray(Ech[0].cpu().numpy().reshape(-1)) if Ech is not None else None
+                nx, ny = self.structured_grid_shape()
+                _lib.call('femol_plan_set_matrix_free', self._plan_view, nx, ny, hb.ctypes.data,
+                          hc.ctypes.data if hc is not None else None, xp, _lib.ptr(mask), _lib.ptr(self._Kv))
+                _lib.call('femol_gmg_setup', self._gmg2, _lib.ptr(Ebh), _lib.ptr(Ech), xp, _lib.ptr(self._Kv), _lib.stream())
+                self._gmg2_refs = (Ebh, Ech, mask)
             self._gmg_stale = False
         return self._gmg
+
+    def _hourglass_enabled(self):
+        h = self.gmg_hourglass
+        if self.N_dof != 6 or not self.matrix_free or not self.structured_grid_shape() or not h:
+            return False
+        if h != 'auto':
+            return True
+        nx, ny = self.structured_grid_shape()
+        self._fixed_mask()
+        if self._mask_host is None:
+            return float(self.ho) >= 8.0 * float(self.mesh.element_size())
+        m = self._mask_host.reshape(ny + 1, nx + 1)
+        edge = np.concatenate([m[0], m[-1], m[:, 0], m[:, -1]])
+        free_edge = bool(((edge >> 2) & 1).min() == 0)      # some boundary node is free to move in w
+        return free_edge and float(self.ho) >= 8.0 * float(self.mesh.element_size())
+
+    def _destroy_gmg(self):
+        L = _lib.load()
+        if getattr(self, '_gmg', None) is not None:
+            L.femol_gmg_destroy(self._gmg)
+            self._gmg = None
+        if getattr(self, '_gmg2', None) is not None:
+            L.femol_gmg_destroy(self._gmg2)
+            self._gmg2 = None
+        if getattr(self, '_plan_view', None) is not None:
+            L.femol_plan_destroy(self._plan_view)
+            self._plan_view = None
 
     def _displacement_solve(self, verbose):
         """FEM.py:201-214"""

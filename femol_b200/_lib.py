@@ -49,6 +49,8 @@ SIGNATURES = {
     'femol_gmg_setup': (c_int, [P, P, P, P, P, P]),
     'femol_gmg_info': (c_int, [P, ctypes.POINTER(c_i64)]),
     'femol_gmg_apply': (c_int, [P, P, P, P]),
+    'femol_gmg_attach_modulated': (c_int, [P, P]),
+    'femol_plan_create_view': (c_int, [P, ctypes.POINTER(c_vp)]),
     'femol_pcg_gmg_workspace_doubles': (c_i64, [P]),
     'femol_pcg_gmg': (c_int, [P, P, P, P, P, c_dbl, c_int, P, ctypes.POINTER(c_int), ctypes.POINTER(c_dbl), P]),
     'femol_dist_unique_id': (c_int, [P]),

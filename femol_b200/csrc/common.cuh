@@ -65,6 +65,7 @@ struct femol_plan {
     int sm_count;
     femol_matrix_free* mf;  // host struct, optional (femol_plan_set_matrix_free)
     int64_t grid_nx, grid_ny;  // > 0: the mesh is an nx x ny rectangle_Q4 grid (femol_plan_set_grid)
+    bool is_view;              // shares the device arrays of another plan (femol_plan_create_view): owns only `mf`
 };
 
 // Deterministic grid reduction scratch: FEMOL_RED_SLOTS partial slots + a ticket counter.

@@ -57,6 +57,8 @@ struct femol_gmg {
     int cluster_size;    // ... CTAs per cluster (0: unavailable)
     int hint_iters;      // CG iterations of the previous solve with this hierarchy (sizes the first batch)
     bool f32_levels;     // coarse-level operators stored in single precision for the smoother products (FEMOL_GMG_F32)
+    femol_gmg* mod;      // hierarchy of the sign-modulated operator S K S (femol_gmg_attach_modulated) or NULL
+    double *mod_r, *mod_z;  // S r and the correction of that hierarchy
 };
 
 namespace {
@@ -386,6 +388,19 @@ prolong_add_kernel(int64_t nxf64, int64_t nyf64, int64_t nxc64, const uint8_t* _
             if (!((fm >> d) & 1u)) o.x += vx;
             if (!((fm >> (d + 1)) & 1u)) o.y += vy;
             *reinterpret_cast<double2*>(out + (size_t)t * ND + d) = o;
+        }
+    }
+}
+
+// out (+)= S in, S = (-1)^(i + j) per grid node (nodes x-fastest, npx per row)
+__global__ void __launch_bounds__(256)
+sign_modulate(int64_t n_nodes, int npx, int nd, const double* __restrict__ in, double* __restrict__ out, int accumulate) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_nodes; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t / npx), i = (int)(t - (int64_t)j * npx);
+        const double s = ((i + j) & 1) ? -1.0 : 1.0;
+        for (int d = 0; d < nd; ++d) {
+            const double v = s * in[t * nd + d];
+            out[t * nd + d] = accumulate ? out[t * nd + d] + v : v;
         }
     }
 }
@@ -1002,6 +1017,22 @@ bool femol_gmg_first_sweep(femol_gmg* g, const double** dinv, double* omega) {
     return true;
 }
 
+// Attach the hierarchy of S K S, S = diag((-1)^(i+j)) over the grid nodes (all dofs of a node share the sign): built
+// by the caller with femol_gmg_create / femol_gmg_setup from the element matrix S_e Ke S_e on a plan VIEW whose
+// matrix-free descriptor carries that element matrix.  NULL detaches.  `g` does not own `mod`.
+extern "C" int femol_gmg_attach_modulated(femol_gmg* g, femol_gmg* mod) {
+    FEMOL_REQUIRE(g, "femol_gmg_attach_modulated: null hierarchy");
+    if (!mod) { g->mod = nullptr; return FEMOL_OK; }
+    FEMOL_REQUIRE(mod->nd == g->nd && mod->lv[0].nx == g->lv[0].nx && mod->lv[0].ny == g->lv[0].ny && !mod->mod,
+                  "femol_gmg_attach_modulated: hierarchies of different grids");
+    if (!g->mod_r) {
+        FEMOL_CUDA_CHECK(cudaMalloc(&g->mod_r, g->lv[0].n * sizeof(double)));
+        FEMOL_CUDA_CHECK(cudaMalloc(&g->mod_z, g->lv[0].n * sizeof(double)));
+    }
+    g->mod = mod;
+    return FEMOL_OK;
+}
+
 // remembers the CG iteration count of the last solve (set >= 0 stores, set < 0 only reads)
 int femol_gmg_iteration_hint(femol_gmg* g, int set) {
     if (set >= 0) g->hint_iters = set;
@@ -1013,6 +1044,22 @@ int femol_gmg_iteration_hint(femol_gmg* g, int set) {
 int femol_gmg_vcycle_internal(femol_gmg* g, const double* r, double* z, cudaStream_t st, double* rz_out, double* red_ws,
                               bool* rz_fused, bool presmoothed) {
     if (rz_fused) *rz_fused = false;
+    if (g->mod) {
+        // z = V(r) + S V_h(S r): the second cycle works on the sign-modulated operator S K S, whose smooth functions
+        // are the hourglass (checkerboard x smooth envelope) functions of K - the low-energy family of the
+        // reference's selectively integrated Q4 plate that neither the smoother nor the coarse grids of K see
+        int rc = g->nd == 2 ? vcycle<2>(g, 0, r, z, st, presmoothed) : vcycle<6>(g, 0, r, z, st, presmoothed);
+        if (rc != FEMOL_OK) return rc;
+        const Level& L0 = g->lv[0];
+        const int grid = grid_for(L0.n_nodes);
+        sign_modulate<<<grid, 256, 0, st>>>(L0.n_nodes, (int)L0.nx + 1, g->nd, r, g->mod_r, 0);
+        FEMOL_LAUNCH_CHECK();
+        rc = g->nd == 2 ? vcycle<2>(g->mod, 0, g->mod_r, g->mod_z, st, false) : vcycle<6>(g->mod, 0, g->mod_r, g->mod_z, st, false);
+        if (rc != FEMOL_OK) return rc;
+        sign_modulate<<<grid, 256, 0, st>>>(L0.n_nodes, (int)L0.nx + 1, g->nd, g->mod_z, z, 1);
+        FEMOL_LAUNCH_CHECK();
+        return FEMOL_OK;
+    }
     return g->nd == 2 ? vcycle<2>(g, 0, r, z, st, presmoothed, rz_out, red_ws, rz_fused)
                       : vcycle<6>(g, 0, r, z, st, presmoothed, rz_out, red_ws, rz_fused);
 }
@@ -1030,6 +1077,7 @@ extern "C" int femol_gmg_destroy(femol_gmg* g) {
     cudaFree(g->coarse_inv);
     cudaFree(g->child_g);
     cudaFree(g->d_desc);
+    cudaFree(g->mod_r); cudaFree(g->mod_z);
     delete g;
     return FEMOL_OK;
 }
@@ -1121,6 +1169,7 @@ extern "C" int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t f
         g->cluster_from = g->solo_from = g->n_levels;
         g->cluster_size = 0;
         g->hint_iters = 0;
+        g->mod = nullptr; g->mod_r = nullptr; g->mod_z = nullptr;
         const char* env_mb = getenv("FEMOL_GMG_CLUSTER_MB");
         const double cluster_mb = env_mb ? atof(env_mb) : 0.0;   // OFF by default: with PDL launches plain kernels win (cfg 2, it/s: off 62-67, 0.7 MB 60-63, 12 MB 47)
         const char* env_solo = getenv("FEMOL_GMG_SOLO_NODES");

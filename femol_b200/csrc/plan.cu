@@ -252,6 +252,7 @@ int exclusive_scan(int32_t* data, int64_t n, cudaStream_t st) {
 
 extern "C" int femol_plan_destroy(femol_plan_t p) {
     if (!p) return FEMOL_OK;
+    if (p->is_view) { delete p->mf; delete p; return FEMOL_OK; }
     cudaFree(p->conn); cudaFree(p->n2e_ptr); cudaFree(p->n2e_idx); cudaFree(p->adj_ptr); cudaFree(p->adj_idx);
     cudaFree(p->src_ptr); cudaFree(p->src); cudaFree(p->src_ell);
     delete p->mf;
@@ -441,5 +442,17 @@ extern "C" int femol_plan_set_grid(femol_plan_t p, int64_t nx, int64_t ny) {
         return FEMOL_E_ARG;
     }
     p->grid_nx = nx; p->grid_ny = ny;
+    return FEMOL_OK;
+}
+
+// A second handle on the same symbolic data with its own matrix-free descriptor (femol_plan_set_matrix_free): the
+// sign-modulated operator S K S of the hourglass hierarchy lives on the same mesh as K.  The view must be destroyed
+// before the plan it was made from.
+extern "C" int femol_plan_create_view(femol_plan_t p, femol_plan_t* out) {
+    FEMOL_REQUIRE(p && out, "femol_plan_create_view: null argument");
+    femol_plan* v = new femol_plan(*p);
+    v->mf = nullptr;
+    v->is_view = true;
+    *out = v;
     return FEMOL_OK;
 }

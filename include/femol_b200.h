@@ -119,6 +119,9 @@ int femol_spmv_csr(int64_t n_rows, const int32_t* indptr, const int32_t* indices
  * Synchronous; nx = 0 clears; FEMOL_E_ARG if the connectivity is in another order. */
 int femol_plan_set_grid(femol_plan_t plan, int64_t nx, int64_t ny);
 
+/* A second handle on the same symbolic plan with its own matrix-free descriptor (destroy it before the plan). */
+int femol_plan_create_view(femol_plan_t plan, femol_plan_t* view_out);
+
 /* Matrix-free K for the solvers on structured rectangle_Q4 meshes (nodes x-fastest, element e = i*ny + j):
  * declares that the value array `vals` equals sum_e (xpow_e * e_base [or e_base + xpow_e * e_coat]) with the
  * Dirichlet mask `fixed` applied — i.e. the arguments of the femol_assemble call that produced it.  femol_pcg /
@@ -159,7 +162,18 @@ int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t fine_plan, c
 int femol_gmg_destroy(femol_gmg_t gmg);
 int femol_gmg_setup(femol_gmg_t gmg, const double* e_base, const double* e_coat, const double* xpow,
                     const double* fine_vals, void* stream);
-int femol_gmg_info(femol_gmg_t gmg, int64_t* h_info); /* [0] = levels, then (nx, ny) per level */
+int femol_gmg_info(femol_gmg_t gmg, int64_t* h_info);
+
+/* Hourglass correction for the reference's Q4 Mindlin plate (shear integrated with one point, elements.py:1029-1054):
+ * its assembled operator has a family of low-energy modes w = (-1)^(i+j) x smooth envelope that are only restrained
+ * through the boundary conditions (plates with free edges), invisible to the smoother and to bilinear coarse grids;
+ * multigrid-CG then needs O(n_x) iterations.  `mod` is a second hierarchy built with femol_gmg_create / _setup for
+ * the sign-modulated operator S K S (element matrix S_e Ke S_e, S_e = diag(+,-,+,-) over the element's nodes) on a
+ * plan view; the preconditioner becomes z = V(r) + S V_mod(S r) and the iteration count is mesh-independent again.
+ * NULL detaches; the caller owns `mod`. */
+int femol_gmg_attach_modulated(femol_gmg_t gmg, femol_gmg_t mod);
+
+/* [0] = levels, then (nx, ny) per level */
 int femol_gmg_apply(femol_gmg_t gmg, const double* r, double* z, void* stream); /* z = V-cycle(r) */
 int64_t femol_pcg_gmg_workspace_doubles(femol_plan_t plan);
 int femol_pcg_gmg(femol_plan_t plan, femol_gmg_t gmg, const double* vals, const double* f, double* u, double rtol,

@@ -959,3 +959,58 @@ def test_result_files(F, golden, tmp_path, monkeypatch):
     back = load_vtk(str(tmp_path / 'vibe_mesh.vtk'))
     assert np.allclose(back.cell_data['X_real']['quad'], m2.cell_data['X']['quad'] ** 3, rtol=1e-15)
     assert np.array_equal(np.load(str(tmp_path / 'vibe_eigs.npy')), np.array(vibe.lmbds))
+
+
+def _cantilever_plate(F, n, t=0.25):
+    mesh = F.mesh.rectangle_Q4(1.0, 1.0, n, n)
+    p = F.FEM_Problem('displacement', 'plate', mesh)
+    p.define_materials(F.materials.isotropic_bending_benchmark()); p.define_tensors(t)
+    p.add_fixed_domain(F.domains.inside_box([0], [[0, 1.]]))
+    p.add_forces([0, 0, -1.0, 0, 0, 0], F.domains.inside_box([1.], [[0.45, 0.55]]))
+    p.solver_rtol = 1e-8
+    return p
+
+
+def test_hourglass_hierarchy_on_plates_with_free_edges(F):
+    """The reference's Q4 Mindlin plate (shear at one point, elements.py:1029-1054) has a low-energy family
+    w = (-1)^(i+j) x smooth envelope that only the boundary conditions restrain: on a cantilever plate multigrid-CG
+    needs O(n) iterations.  With the second hierarchy on S K S (femol_gmg_attach_modulated, 'auto' on plates with free
+    edges and a thickness of at least 8 element sizes) the count is mesh-independent, the preconditioner stays
+    symmetric positive and the solution is the same."""
+    import torch
+    its = {}
+    for hg in (False, 'auto'):
+        for n in (40, 80):
+            p = _cantilever_plate(F, n)
+            p.gmg_hourglass = hg
+            U = p.solve_device()
+            assert p.solver_info['converged'] and p.solver_info['preconditioner'] == 'gmg'
+            its[hg, n] = p.solver_info['iterations']
+            if n == 80:
+                sol = {**locals().get('sol', {}), hg: U.cpu().numpy().copy()}
+    assert its['auto', 80] <= its['auto', 40] + 8, its                      # mesh-independent
+    assert its[False, 80] > 1.5 * its[False, 40] and its['auto', 80] < its[False, 80] // 2, its
+    assert rel(sol['auto'], sol[False]) < 1e-5
+    # symmetric positive preconditioner with the second cycle attached
+    p = _cantilever_plate(F, 24)
+    p.gmg_hourglass = True            # t / h = 6 here: below the 'auto' threshold
+    p.assemble('K')
+    g = p._gmg_ready()
+    assert p._gmg2 is not None
+    thin = _cantilever_plate(F, 24, t=0.01)
+    thin.assemble('K'); thin._gmg_ready()
+    assert thin._gmg2 is None         # 'auto' stays off far below 8 element sizes
+    rng = np.random.default_rng(2)
+    R = rng.standard_normal((2, p.device.n)); R[:, p.fixed_dofs()] = 0
+    Z = []
+    for r in R:
+        rd = torch.from_numpy(r).cuda(); zd = torch.empty_like(rd)
+        F._lib.call('femol_gmg_apply', g, rd.data_ptr(), zd.data_ptr(), F._lib.stream())
+        Z.append(zd.cpu().numpy())
+    assert abs(R[0] @ Z[1] - R[1] @ Z[0]) < 1e-9 * abs(R[0] @ Z[1]) + 1e-13 * np.linalg.norm(Z[0]) * np.linalg.norm(R[1])
+    assert R[0] @ Z[0] > 0 and R[1] @ Z[1] > 0
+    # fully supported plates keep the single hierarchy under 'auto'
+    ps, _ = _gmg_problem(F, 24, 12, 'plate')
+    ps.add_fixed_domain(F.domains.inside_box([[0, 24.]], [0, 12.]), ddls=[2]); ps.add_fixed_domain(F.domains.inside_box([0, 24.], [[0, 12.]]), ddls=[2])
+    ps.assemble('K'); ps._gmg_ready()
+    assert ps._gmg2 is None
