@@ -29,6 +29,8 @@ def run(n, bc, load, model='plate', t=0.1):
     dom = box([1.], [[0.45, 0.55]]) if load == 'tip' else box([[0.001, 0.999]], [[0.001, 0.999]])
     p.add_forces(f, dom)
     p.solver_rtol = 1e-8
+    if os.environ.get('NU'):
+        p.gmg_smoothing_steps = int(os.environ['NU'])
     if os.environ.get('HOURGLASS'):
         p.gmg_hourglass = {'0': False, '1': True}.get(os.environ['HOURGLASS'], 'auto')
     p.solve_device()
