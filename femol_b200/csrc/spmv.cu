@@ -93,48 +93,68 @@ spmv_block2_f32_kernel(int64_t n_nodes, const int32_t* __restrict__ adj_ptr, con
     const int64_t stride = (int64_t)gridDim.x * blockDim.x / G;
     const int64_t n_iter = (n_nodes + stride - 1) / stride;
     const double2* __restrict__ x2 = reinterpret_cast<const double2*>(x);
-    for (int64_t it = 0; it < n_iter; ++it) {
-        const int64_t i = node0 + it * stride;
-        double a0 = 0.0, a1 = 0.0;
-        if (i < n_nodes) {
-            const int pb = __ldg(&adj_ptr[i]);
-            const int len = __ldg(&adj_ptr[i + 1]) - pb;
-            for (int k0 = g; k0 < len; k0 += 4 * G) {
-                int32_t j[4]; float4 a[4];
+    // Two nodes per thread in flight and every load level (row pointers -> column indices + blocks -> gathered x)
+    // issued for both before the first use: the kernel is a chain of dependent L2 / DRAM round trips, not a stream
+    constexpr int U = 2, Q = 3;      // Q slots per lane cover rows of up to Q * G = 12 node blocks; longer rows: tail loop
+    for (int64_t it = 0; it < n_iter; it += U) {
+        int64_t i[U]; int pb[U], len[U];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int k = k0 + q * G;
-                    const bool ok = k < len;
-                    j[q] = ok ? __ldg(&adj_idx[pb + k]) : -1;
-                    a[q] = ok ? __ldcs(&blk[pb + k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < U; ++u) {
+            i[u] = node0 + (it + u) * stride;
+            const bool ok = it + u < n_iter && i[u] < n_nodes;
+            pb[u] = ok ? __ldg(&adj_ptr[i[u]]) : 0;
+            len[u] = ok ? __ldg(&adj_ptr[i[u] + 1]) - pb[u] : 0;
+        }
+        int32_t j[U][Q]; float4 a[U][Q];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int k = g + q * G;
+                const bool ok = k < len[u];
+                j[u][q] = ok ? __ldg(&adj_idx[pb[u] + k]) : -1;
+                a[u][q] = ok ? __ldcs(&blk[pb[u] + k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        double2 bx[U][Q];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < Q; ++q) bx[u][q] = j[u][q] >= 0 ? __ldg(&x2[j[u][q]]) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                a0 += (double)a[u][q].x * bx[u][q].x; a0 += (double)a[u][q].y * bx[u][q].y;
+                a1 += (double)a[u][q].z * bx[u][q].x; a1 += (double)a[u][q].w * bx[u][q].y;
+            }
+            for (int k = g + Q * G; k < len[u]; k += G) {      // rows longer than Q * G node blocks
+                const int32_t jj = __ldg(&adj_idx[pb[u] + k]);
+                const float4 aa = __ldcs(&blk[pb[u] + k]);
+                const double2 b = __ldg(&x2[jj]);
+                a0 += (double)aa.x * b.x; a0 += (double)aa.y * b.y;
+                a1 += (double)aa.z * b.x; a1 += (double)aa.w * b.y;
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            }
+            if (g == 0 && len[u] > 0) {
+                const int64_t ii = i[u];
+                double2 out = make_double2(a0, a1);
+                if (MODE >= 1) {
+                    const double2 r = __ldg(reinterpret_cast<const double2*>(rhs) + ii);
+                    out.x = r.x - a0; out.y = r.y - a1;
                 }
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (j[q] >= 0) {
-                        const double2 b = __ldg(&x2[j[q]]);
-                        a0 += (double)a[q].x * b.x; a0 += (double)a[q].y * b.y;
-                        a1 += (double)a[q].z * b.x; a1 += (double)a[q].w * b.y;
-                    }
+                if (MODE == 2) {
+                    const double2 d0 = __ldg(reinterpret_cast<const double2*>(dinv) + 2 * ii);
+                    const double2 d1 = __ldg(reinterpret_cast<const double2*>(dinv) + 2 * ii + 1);
+                    const double2 xi = __ldg(&x2[ii]);
+                    out = make_double2(xi.x + omega * (d0.x * out.x + d0.y * out.y), xi.y + omega * (d1.x * out.x + d1.y * out.y));
+                }
+                reinterpret_cast<double2*>(y)[ii] = out;
             }
-        }
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-        }
-        if (g == 0 && i < n_nodes) {
-            double2 out = make_double2(a0, a1);
-            if (MODE >= 1) {
-                const double2 r = __ldg(reinterpret_cast<const double2*>(rhs) + i);
-                out.x = r.x - a0; out.y = r.y - a1;
-            }
-            if (MODE == 2) {
-                const double2 d0 = __ldg(reinterpret_cast<const double2*>(dinv) + 2 * i);
-                const double2 d1 = __ldg(reinterpret_cast<const double2*>(dinv) + 2 * i + 1);
-                const double2 xi = __ldg(&x2[i]);
-                out = make_double2(xi.x + omega * (d0.x * out.x + d0.y * out.y), xi.y + omega * (d1.x * out.x + d1.y * out.y));
-            }
-            reinterpret_cast<double2*>(y)[i] = out;
         }
     }
 }
