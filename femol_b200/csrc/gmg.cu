@@ -39,6 +39,7 @@ struct Level {
     float* vals32;      // the same values in single precision (regular levels >= 1 of the mixed-precision V-cycle) or NULL
     double* dinv;       // [n_nodes][ND][ND]
     double *r, *e, *t;  // work vectors (level 0: r, e supplied by the caller through vcycle)
+    double *r2, *e2;    // second coarse visit of the F / W cycle (levels >= 1)
 };
 
 }  // namespace
@@ -57,6 +58,8 @@ struct femol_gmg {
     int cluster_size;    // ... CTAs per cluster (0: unavailable)
     int hint_iters;      // CG iterations of the previous solve with this hierarchy (sizes the first batch)
     bool f32_levels;     // coarse-level operators stored in single precision for the smoother products (FEMOL_GMG_F32)
+    int cycle;           // 0 V-cycle, 1 F-cycle, 2 W-cycle (nu = 1 path; FEMOL_GMG_CYCLE = V | F | W)
+    int cycle_depth;     // coarse levels 1 .. cycle_depth get the second visit, deeper ones a plain V-cycle
     femol_gmg* mod;      // hierarchy of the sign-modulated operator S K S (femol_gmg_attach_modulated) or NULL
     double *mod_r, *mod_z;  // S r and the correction of that hierarchy
 };
@@ -403,6 +406,10 @@ sign_modulate(int64_t n_nodes, int npx, int nd, const double* __restrict__ in, d
             out[t * nd + d] = accumulate ? out[t * nd + d] + v : v;
         }
     }
+}
+
+__global__ void __launch_bounds__(256) axpy_kernel(int64_t n, const double* __restrict__ a, double* __restrict__ b) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) b[i] += a[i];
 }
 
 // ---- smoother ------------------------------------------------------------------------------------------------------
@@ -940,7 +947,8 @@ int smooth(femol_gmg* g, int l, const double* r, double* e, bool zero_start, cud
 // `presmoothed`: e already holds the first sweep omega Dinv r (written by the restriction that produced r)
 template <int ND>
 int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, bool presmoothed = false,
-           double* rz_out = nullptr, double* red_ws = nullptr, bool* rz_fused = nullptr) {
+           double* rz_out = nullptr, double* red_ws = nullptr, bool* rz_fused = nullptr, int cyc = -1) {
+    if (cyc < 0) cyc = g->cycle;     // 0: V, 1: F (second coarse visit is a V-cycle), 2: W
     Level& L = g->lv[l];
     if (g->nu == 1 && l >= 1 && l >= g->cluster_from && presmoothed) return launch_cluster_vcycle<ND>(g, l, r, e, st);
     if (g->nu != 1 && l >= 1 && l >= g->fused_from && g->d_desc) {
@@ -976,8 +984,19 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, boo
                                           (const uint8_t*)L.fixed, (const uint8_t*)C.fixed, (const double*)L.t, C.r,
                                           (const double*)(coarse_regular ? C.dinv : nullptr), g->omega, C.e));
         femol_count_launch();
-        rc = vcycle<ND>(g, l + 1, C.r, C.e, st, coarse_regular);
+        rc = vcycle<ND>(g, l + 1, C.r, C.e, st, coarse_regular, nullptr, nullptr, nullptr, cyc);
         if (rc != FEMOL_OK) return rc;
+        if (cyc > 0 && coarse_regular && l + 1 <= g->cycle_depth) {
+            // second visit of the coarse level: e_c += Cycle(r_c - K_c e_c)
+            const femol_epilogue res2 = {FEMOL_EPI_RESIDUAL, C.r, nullptr, 0.0, nullptr, nullptr};
+            rc = C.vals32 ? femol_spmv_f32_epilogue_launch(C.plan, C.vals32, C.e, C.r2, res2, st)
+                          : femol_apply_epilogue_launch(C.plan, C.vals, C.e, C.r2, res2, st);
+            if (rc != FEMOL_OK) return rc;
+            rc = vcycle<ND>(g, l + 1, C.r2, C.e2, st, false, nullptr, nullptr, nullptr, cyc == 1 ? 0 : cyc);
+            if (rc != FEMOL_OK) return rc;
+            axpy_kernel<<<grid_for(C.n), 256, 0, st>>>(C.n, C.e2, C.e);
+            FEMOL_LAUNCH_CHECK();
+        }
         if (femol_apply_has_jacobi(L.plan, L.vals)) {
             FEMOL_CUDA_CHECK(femol_launch_pdl(prolong_add_kernel<ND>, dim3(grid_for(L.n_nodes)), dim3(256), 0, st, L.nx, L.ny, C.nx,
                                               (const uint8_t*)L.fixed, (const double*)C.e, (const double*)e, L.t));
@@ -1070,7 +1089,7 @@ extern "C" int femol_gmg_destroy(femol_gmg* g) {
         Level& L = g->lv[l];
         if (l > 0) {
             femol_plan_destroy(L.plan);
-            cudaFree(L.fixed); cudaFree(L.ke); cudaFree(L.vals); cudaFree(L.vals32); cudaFree(L.r); cudaFree(L.e);
+            cudaFree(L.fixed); cudaFree(L.ke); cudaFree(L.vals); cudaFree(L.vals32); cudaFree(L.r); cudaFree(L.e); cudaFree(L.r2); cudaFree(L.e2);
         }
         cudaFree(L.dinv); cudaFree(L.t);
     }
@@ -1134,6 +1153,8 @@ extern "C" int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t f
             if (g->f32_levels) GCHECK(cudaMalloc(&L.vals32, L.plan->nnz * sizeof(float)));
             GCHECK(cudaMalloc(&L.r, L.n * sizeof(double)));
             GCHECK(cudaMalloc(&L.e, L.n * sizeof(double)));
+            GCHECK(cudaMalloc(&L.r2, L.n * sizeof(double)));
+            GCHECK(cudaMalloc(&L.e2, L.n * sizeof(double)));
         }
         const bool small = L.n <= GMG_COARSE_MAX_DOF && l > 0;
         if (small || (cx == 1 && cy == 1) || l == GMG_MAX_LEVELS - 1) break;
@@ -1170,6 +1191,12 @@ extern "C" int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t f
         g->cluster_size = 0;
         g->hint_iters = 0;
         g->mod = nullptr; g->mod_r = nullptr; g->mod_z = nullptr;
+        {
+            const char* ec = getenv("FEMOL_GMG_CYCLE");
+            g->cycle = (ec && (ec[0] == 'F' || ec[0] == 'f')) ? 1 : (ec && (ec[0] == 'W' || ec[0] == 'w')) ? 2 : 0;
+            const char* ed = getenv("FEMOL_GMG_CYCLE_DEPTH");
+            g->cycle_depth = ed ? atoi(ed) : 99;
+        }
         const char* env_mb = getenv("FEMOL_GMG_CLUSTER_MB");
         const double cluster_mb = env_mb ? atof(env_mb) : 0.0;   // OFF by default: with PDL launches plain kernels win (cfg 2, it/s: off 62-67, 0.7 MB 60-63, 12 MB 47)
         const char* env_solo = getenv("FEMOL_GMG_SOLO_NODES");
