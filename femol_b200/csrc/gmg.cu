@@ -58,7 +58,7 @@ struct femol_gmg {
     int cluster_size;    // ... CTAs per cluster (0: unavailable)
     int hint_iters;      // CG iterations of the previous solve with this hierarchy (sizes the first batch)
     bool f32_levels;     // coarse-level operators stored in single precision for the smoother products (FEMOL_GMG_F32)
-    int cycle;           // 0 V-cycle, 1 F-cycle, 2 W-cycle (nu = 1 path; FEMOL_GMG_CYCLE = V | F | W)
+    int cycle;           // 0 V-cycle, 1 F-cycle (NOT symmetric: experiments only), 2 W-cycle (nu = 1 path; FEMOL_GMG_CYCLE = V | F | W)
     int cycle_depth;     // coarse levels 1 .. cycle_depth get the second visit, deeper ones a plain V-cycle
     femol_gmg* mod;      // hierarchy of the sign-modulated operator S K S (femol_gmg_attach_modulated) or NULL
     double *mod_r, *mod_z;  // S r and the correction of that hierarchy
