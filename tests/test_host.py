@@ -235,3 +235,38 @@ def test_vtk_round_trip(tmp_path, kind):
         assert np.array_equal(back.point_data[k], mesh.point_data[k])
     for k in ('X', 'zc'):
         assert np.array_equal(back.cell_data[k][ctype], mesh.cell_data[k][ctype])
+
+
+def test_load_vtk_ascii(tmp_path):
+    """load_vtk also reads ASCII legacy files (e.g. written by other tools): one quad and one triangle with data."""
+    from femol_b200.mesh import load_vtk
+    text = '''# vtk DataFile Version 3.0
+hand written
+ASCII
+DATASET UNSTRUCTURED_GRID
+POINTS 5 double
+0 0 0  1 0 0  1 1 0
+0 1 0  2 0.5 0
+CELLS 2 9
+4 0 1 2 3
+3 1 4 2
+CELL_TYPES 2
+9
+5
+POINT_DATA 5
+SCALARS Ux double 1
+LOOKUP_TABLE default
+0.0 0.1 0.2 0.3 0.4
+CELL_DATA 2
+SCALARS X double 1
+LOOKUP_TABLE default
+0.25 0.75
+'''
+    path = tmp_path / 'ascii.vtk'
+    path.write_text(text)
+    mesh = load_vtk(str(path))
+    assert mesh.points.shape == (5, 3) and np.array_equal(mesh.cells['quad'], [[0, 1, 2, 3]])
+    assert np.array_equal(mesh.cells['triangle'], [[1, 4, 2]])
+    assert np.allclose(mesh.point_data['Ux'], [0.0, 0.1, 0.2, 0.3, 0.4])
+    vals = {k: mesh.cell_data['X'][k][0] for k in mesh.contains}
+    assert vals == {'quad': 0.25, 'triangle': 0.75}
