@@ -29,6 +29,7 @@ def run(n, bc, load, model='plate', t=0.1):
     dom = box([1.], [[0.45, 0.55]]) if load == 'tip' else box([[0.001, 0.999]], [[0.001, 0.999]])
     p.add_forces(f, dom)
     p.solver_rtol = 1e-8
+    p.solver_max_iter = int(os.environ.get('MAXIT', '200000'))
     if os.environ.get('NU'):
         p.gmg_smoothing_steps = int(os.environ['NU'])
     if os.environ.get('HOURGLASS'):
@@ -60,6 +61,11 @@ if len(sys.argv) > 1 and sys.argv[1] == 'supported':
 if len(sys.argv) > 1 and sys.argv[1] == 'thin':
     for t in (0.001, 0.0025, 0.005, 0.01, 0.02, 0.05):
         run(200, 'cantilever', 'uniform', t=t)
+    sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == 'verythin':
+    for t in (0.001, 0.0025, 0.01):
+        run(200, 'cantilever', 'uniform', t=t)
+        run(200, 'ss', 'uniform', t=t)
     sys.exit(0)
 for n in (50, 100, 200, 400):
     run(n, 'cantilever', 'tip')
