@@ -49,7 +49,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // straight-line (no loop around the multiply), so the element-matrix operands are read from the constant bank
 // where they are used instead of being hoisted into, and spilled from, registers.
 template <int ND, bool COAT, int TI, int TJ, int NT, int NPT, int MODE>
-__global__ void __launch_bounds__(TI * TJ / NPT, ND == 2 ? (COAT ? 2 : 3) : (COAT ? 1 : 2))
+__global__ void __launch_bounds__(TI * TJ / NPT, ND == 2 ? (COAT ? 4 : 5) : (COAT ? 1 : 2))
 stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int ny, int tiles_i, int n_tiles, int cta0,
                     const double* __restrict__ xpow, const uint8_t* __restrict__ fixed,
                     const double* __restrict__ u, double* __restrict__ y, const double* __restrict__ dot_with,
@@ -252,7 +252,7 @@ stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int
 template <int ND, bool COAT, int MODE>
 int launch_stencil_c(femol_plan_t p, const femol_matrix_free* mf, const double* x, double* y, const double* dot_with,
                      double* dot_out, double* red_ws, const femol_epilogue& ep, cudaStream_t st) {
-    constexpr int TI = 32, TJ = ND == 2 ? 16 : 8, NT = 4, NPT = ND == 2 ? 2 : 1;
+    constexpr int TI = 32, TJ = 8, NT = 4, NPT = ND == 2 ? 2 : 1;
     constexpr int WW = (TI + 1) * (TJ + 1);
     constexpr size_t smem = (size_t)NT * ((TJ + 2) * (TI + 2) * ND + WW + (WW & 1)) * sizeof(double);
     static bool configured = false;
