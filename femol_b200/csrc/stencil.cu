@@ -113,10 +113,16 @@ stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int
 #pragma unroll
     for (int k = 0; k < NT; ++k) {
         if (first + k >= n_tiles) break;     // uniform across the CTA
-        if (k == 0) cp_async_wait<NT - 1>();
-        else if (k == 1) cp_async_wait<(NT > 2 ? NT - 2 : 0)>();
-        else if (k == 2) cp_async_wait<(NT > 3 ? NT - 3 : 0)>();
-        else cp_async_wait<0>();
+        switch (NT - 1 - k) {       // groups that may still be in flight while tile k is consumed (k is a constant here)
+            case 7: cp_async_wait<7>(); break;
+            case 6: cp_async_wait<6>(); break;
+            case 5: cp_async_wait<5>(); break;
+            case 4: cp_async_wait<4>(); break;
+            case 3: cp_async_wait<3>(); break;
+            case 2: cp_async_wait<2>(); break;
+            case 1: cp_async_wait<1>(); break;
+            default: cp_async_wait<0>(); break;
+        }
         double* s_u = s_mem + k * STAGE;
         const double* s_w = s_u + PJ * PI * ND;
         uint32_t mine = 0u;
@@ -252,7 +258,7 @@ stencil_tile_kernel(const __grid_constant__ StencilMat<ND, COAT> km, int nx, int
 template <int ND, bool COAT, int MODE>
 int launch_stencil_c(femol_plan_t p, const femol_matrix_free* mf, const double* x, double* y, const double* dot_with,
                      double* dot_out, double* red_ws, const femol_epilogue& ep, cudaStream_t st) {
-    constexpr int TI = 32, TJ = 8, NT = 4, NPT = ND == 2 ? 2 : 1;
+    constexpr int TI = 32, TJ = 8, NT = 2, NPT = ND == 2 ? 2 : 1;
     constexpr int WW = (TI + 1) * (TJ + 1);
     constexpr size_t smem = (size_t)NT * ((TJ + 2) * (TI + 2) * ND + WW + (WW & 1)) * sizeof(double);
     static bool configured = false;
