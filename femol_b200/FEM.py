@@ -16,6 +16,7 @@ matrices on demand (bit-identical pattern: sorted int32 indices, explicit zeros 
 fallback: without the CUDA library or a GPU every compute call raises.
 """
 import ctypes
+import warnings
 
 import numpy as np
 import scipy.sparse
@@ -28,6 +29,41 @@ from .laminate import Layup
 from .mesh import Mesh
 
 __all__ = ['FEM_Problem', 'Mesh', 'Layup']
+
+
+class _TrackedVector(np.ndarray):
+    """`problem.F` as handed back after an assembly: an ordinary float64 array whose in-place edits
+    (`F[i] = v`, `F[a:b] += w`, writes through views) raise a shared dirty flag, so the next assembly re-applies
+    the boundary conditions and re-uploads it - the reference re-reads `self.F` on every assembly (FEM.py:536-544);
+    checksumming 4 M entries per SIMP iteration instead would cost 2 - 3 ms."""
+
+    def __new__(cls, data):
+        obj = np.asarray(data, dtype=np.float64).view(cls)
+        obj._flag = [False]
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._flag = getattr(obj, '_flag', None) or [False]
+
+    def __setitem__(self, key, value):
+        self._flag[0] = True
+        super().__setitem__(key, value)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
+        plain = [np.asarray(a) if isinstance(a, _TrackedVector) else a for a in inputs]
+        if out is not None:
+            for o in out:
+                if isinstance(o, _TrackedVector):
+                    o._flag[0] = True
+            kwargs['out'] = tuple(np.asarray(o) if isinstance(o, _TrackedVector) else o for o in out)
+        res = getattr(ufunc, method)(*plain, **kwargs)
+        if out is not None and len(out) == 1 and isinstance(out[0], _TrackedVector) and res is kwargs['out'][0]:
+            return out[0]              # `F += w` must rebind the name to the tracked array, not to a plain view
+        return res
+
+    @property
+    def dirty(self):
+        return self._flag[0]
 
 _PRECOND = {'none': _lib.PRECOND_NONE, 'jacobi': _lib.PRECOND_JACOBI, 'block_jacobi': _lib.PRECOND_BLOCK_JACOBI}
 
@@ -125,6 +161,11 @@ class FEM_Problem(object):
         # solver controls (no reference counterpart: spsolve is direct)
         self.solver_rtol = 1e-10
         self.solver_max_iter = 200000
+        # a solve that stops without reaching its tolerance: 'warn' (FemolConvergenceWarning, results are still
+        # returned), 'raise' (FemolError) or 'ignore'.  PCG status 3 (recurrence converged, true residual at its
+        # attainable floor ~ eps * cond(K)) counts as converged up to `stagnation_bound`
+        self.on_nonconvergence = 'warn'
+        self.stagnation_bound = 1e-6
         # 'auto': geometric multigrid on rectangle_Q4-ordered structured meshes, block-Jacobi otherwise;
         # 'gmg' | 'block_jacobi' | 'jacobi' | 'none' force one
         self.preconditioner = 'auto'
@@ -160,6 +201,7 @@ class FEM_Problem(object):
         self._K_host = self._M_host = None
         self._U_dev = None
         self._X_modal = None  # last eigenvector block (warm start)
+        self._epoch = 0
         self._mask_key = None
         self._mask_dev = None
         self._mask_host = None
@@ -251,7 +293,28 @@ class FEM_Problem(object):
         return self._dev
 
     def _bc_key(self):
-        return (len(self.fixed_domains), tuple(tuple(np.asarray(d).tolist()) for d in self.fixed_ddls))
+        """Identity of the Dirichlet set: the domain callables themselves (replacing one in place invalidates the
+        cached mask / fixed dofs / multigrid hierarchy / F), their dof lists and the invalidate() epoch."""
+        return (self._epoch, tuple(id(d) for d in self.fixed_domains),
+                tuple(tuple(np.asarray(d).tolist()) for d in self.fixed_ddls))
+
+    def invalidate(self):
+        """Drop every cache derived from the mesh geometry, the domains and the loads (call after editing
+        `mesh.points` in place; replaced domains / forces / `F` edits are detected without it)."""
+        self._epoch += 1
+        self._E.clear()
+        self._E_host.clear()
+        self._F_key = None
+        self._grid_shape = None
+        self._gmg_stale = True
+        if self._dev is not None:
+            self._dev.xy.copy_(torch.from_numpy(np.ascontiguousarray(self.mesh.points[:, :2], dtype=np.float64)))
+
+    def _report_nonconvergence(self, message):
+        if self.on_nonconvergence == 'raise':
+            raise _lib.FemolError(message)
+        if self.on_nonconvergence != 'ignore':
+            warnings.warn(message, _lib.FemolConvergenceWarning, stacklevel=3)
 
     def fixed_dofs(self):
         """Sorted unique global dof numbers fixed by the registered domains (cached: the reference
@@ -429,19 +492,18 @@ class FEM_Problem(object):
     def _assemble_F(self):
         """FEM.py:536-544: zero the force at fixed dofs.
 
-        The uploaded array is kept and made read-only: loads change by assigning a new array to `problem.F`
-        (what `add_forces` does, FEM.py:464), which is detected by identity; an in-place edit raises instead of
-        being silently ignored.  (Checksumming the 4 M-entry vector on every assembly cost 2-3 ms per SIMP
-        iteration on cfg 2.)"""
-        key = (self._bc_key(), len(self.forces))
-        if self._F_key == key and self._F_ref is self.F:
+        The uploaded vector is cached.  It is refreshed when `problem.F` was rebound (what `add_forces` does,
+        FEM.py:464; detected by identity), when it was edited in place (`problem.F` is handed back as a
+        `_TrackedVector` whose writes raise a dirty flag) and when the Dirichlet set changed.  (Checksumming the
+        4 M-entry vector on every assembly cost 2-3 ms per SIMP iteration on cfg 2.)"""
+        key = (self._bc_key(), tuple(id(f) for f in self.forces), tuple(id(d) for d in self.force_domains))
+        if self._F_key == key and self._F_ref is self.F and not self.F.dirty:
             return                                   # nothing changed since the last upload
         F = np.array(self.F, dtype=np.float64)       # private copy
         if self.fixed_ddls:
             F[self.fixed_dofs()] = 0
-        F.setflags(write=False)
-        self.F = self._F_ref = F
-        self._F_dev = torch.from_numpy(F.copy()).to(self.device.dev)
+        self._F_dev = torch.from_numpy(F).to(self.device.dev)
+        self.F = self._F_ref = _TrackedVector(F)
         self._F_key = key
 
     @property
@@ -507,10 +569,17 @@ class FEM_Problem(object):
                            _lib.ptr(d.pcg_ws()), ctypes.byref(iters), ctypes.byref(relres), _lib.stream())
         # status 0: converged to rtol; 3: recurrence converged and the TRUE residual sits at its attainable
         # floor (~ eps * cond(K), the level a direct solver reaches too); 1: iteration limit
+        converged = rc == 0 or (rc == _lib.S_STAGNATED and relres.value <= self.stagnation_bound)
         self.solver_info = {'iterations': iters.value, 'relres': relres.value, 'status': rc,
-                            'converged': rc in (0, _lib.S_STAGNATED), 'preconditioner': precond}
+                            'converged': converged, 'preconditioner': precond}
         if rc == _lib.S_BREAKDOWN:
             raise _lib.FemolError('PCG breakdown (matrix not positive definite?) after %d iterations' % iters.value)
+        if not converged:
+            why = ('iteration limit %d reached' % self.solver_max_iter if rc == _lib.S_NOT_CONVERGED else
+                   'stagnated above stagnation_bound = %.1e' % self.stagnation_bound)
+            self._report_nonconvergence('PCG (%s) did not converge: %s after %d iterations, relative residual %.3e '
+                                        '(rtol %.1e); the returned displacement is the last iterate'
+                                        % (precond, why, iters.value, relres.value, self.solver_rtol))
         return self._U_dev
 
     # ---- geometric multigrid (structured Q4 meshes) ---------------------------------------------------
@@ -658,7 +727,14 @@ class FEM_Problem(object):
         lam, rel, its = _lobpcg.lobpcg(ops, m, k, tol=self.modal_tol, max_iter=self.modal_max_iter)
         V = ops.vectors()
         self._X_modal = V.clone()
-        self.solver_info = {'iterations': its, 'relres': rel[:k].copy(), 'block': m}
+        # converged to modal_tol, or stopped at the attainable accuracy (LOBPCG's stall rule) below stagnation_bound
+        worst = float(np.max(rel[:k])) if k else 0.0
+        converged = bool(np.all(np.isfinite(lam[:k]))) and worst <= max(self.modal_tol, self.stagnation_bound)
+        self.solver_info = {'iterations': its, 'relres': rel[:k].copy(), 'block': m, 'converged': converged}
+        if not converged:
+            self._report_nonconvergence('LOBPCG did not converge: %d iterations (limit %d), worst relative residual '
+                                        '%.3e over the %d requested pairs (tol %.1e); the returned pairs are the last '
+                                        'Ritz pairs' % (its, self.modal_max_iter, worst, k, self.modal_tol))
         return lam[:k], V[:, :k].t().contiguous()
 
     def _modal_solve(self, verbose, filtre=0):

@@ -58,6 +58,7 @@ class SIMP_VIBE(object):
         self._filter = None
         self._mask = None
         self._mask_key = None
+        self.unconverged_solves = 0   # SIMP iterations whose eigen-solve stopped short of its tolerance
 
     def set_density(self, X):
         if isinstance(X, dict):
@@ -165,6 +166,7 @@ class SIMP_VIBE(object):
         while not solved:
             self.loop += 1
             self.iterate(v_ref)
+            self.unconverged_solves += 0 if self.FEM.solver_info.get('converged', True) else 1
             if self.archive:
                 self.X = {ctype: self.density()}
                 self.v = self._v.cpu().numpy()

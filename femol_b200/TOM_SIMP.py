@@ -109,6 +109,9 @@ class SIMP_COMP(object):
         self.X = {key: np.ones(self.mesh.cells[key].shape[0]) * volfrac for key in self.mesh.contains}
         self.archive = True          # keep X{k} / d{k} histories in the mesh like the reference (:62-69)
         self.iteration_log = []
+        # SIMP iterations whose linear solve stopped short of its tolerance (each one also raises a
+        # FemolConvergenceWarning, or a FemolError with Problem.on_nonconvergence = 'raise')
+        self.unconverged_solves = 0
         d = self.FEM.device
         self._x = torch.full((d.n_elem,), float(volfrac), dtype=torch.float64, device=d.dev)
         self._dc = torch.empty(d.n_elem, dtype=torch.float64, device=d.dev)
@@ -204,6 +207,7 @@ class SIMP_COMP(object):
             info = dict(self.FEM.solver_info)
             info.update(loop=self.loop, change=self.change, c=self.c)
             self.iteration_log.append(info)
+            self.unconverged_solves += 0 if info.get('converged', True) else 1
             if self.archive:
                 self.X = {ctype: self.density()}
                 self.U = self._U.cpu().numpy()

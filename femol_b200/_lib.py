@@ -53,6 +53,7 @@ SIGNATURES = {
     'femol_plan_create_view': (c_int, [P, ctypes.POINTER(c_vp)]),
     'femol_pcg_gmg_workspace_doubles': (c_i64, [P]),
     'femol_pcg_gmg': (c_int, [P, P, P, P, P, c_dbl, c_int, P, ctypes.POINTER(c_int), ctypes.POINTER(c_dbl), P]),
+    'femol_graph_stats': (c_int, [ctypes.POINTER(c_i64), c_int]),
     'femol_dist_unique_id': (c_int, [P]),
     'femol_dist_init': (c_int, [P, c_int, c_int, ctypes.POINTER(c_vp)]),
     'femol_dist_destroy': (c_int, [P]),
@@ -83,6 +84,11 @@ _lib = None
 
 class FemolError(RuntimeError):
     pass
+
+
+class FemolConvergenceWarning(RuntimeWarning):
+    """An iterative solve (PCG / LOBPCG) stopped without reaching its tolerance.  The reference uses direct
+    solvers (spsolve / eigh), so its callers never check; here the condition is reported instead of silent."""
 
 
 def load():
@@ -126,6 +132,13 @@ def ptr(t):
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def graph_stats(reset=False):
+    """CUDA-graph use of femol_pcg_gmg: captures attempted / instantiated, graph launches, side-stream solves."""
+    out = (c_i64 * 4)()
+    check(load().femol_graph_stats(out, 1 if reset else 0), 'femol_graph_stats')
+    return dict(zip(('captures', 'instantiated', 'graph_launches', 'side_stream_solves'), [int(v) for v in out]))
 
 
 def call(name, *args):

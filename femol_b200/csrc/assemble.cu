@@ -418,13 +418,11 @@ int launch_grid(femol_plan_t p, const double* e_base, const double* e_coat, cons
     if (grid > cap) grid = cap;
     if (e_coat) {
         auto kern = assemble_grid_kernel<ND, true>;
-        static bool configured = false;
-        if (!configured) { FEMOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024)); configured = true; }
+        FEMOL_FUNC_ATTR_PER_DEVICE(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
         kern<<<(int)grid, 128, smem, st>>>((int)p->grid_nx, (int)p->grid_ny, p->adj_ptr, e_base, e_coat, xpow, fixed, vals);
     } else {
         auto kern = assemble_grid_kernel<ND, false>;
-        static bool configured = false;
-        if (!configured) { FEMOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024)); configured = true; }
+        FEMOL_FUNC_ATTR_PER_DEVICE(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
         kern<<<(int)grid, 128, smem, st>>>((int)p->grid_nx, (int)p->grid_ny, p->adj_ptr, e_base, nullptr, xpow, fixed, vals);
     }
     FEMOL_LAUNCH_CHECK();

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include "../../include/femol_b200.h"
 
 #define FEMOL_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
@@ -26,6 +27,20 @@ extern "C" int64_t femol_launch_count(int reset);
     do {                                    \
         femol_count_launch();               \
         FEMOL_CUDA_CHECK(cudaGetLastError()); \
+    } while (0)
+
+// cudaFuncSetAttribute is per device (context): remember it per device, not per process (a process may drive
+// several GPUs, and two host threads may race on the first call; setting it twice is harmless)
+#define FEMOL_FUNC_ATTR_PER_DEVICE(kern, attr, value)                                        \
+    do {                                                                                     \
+        static std::atomic<unsigned long long> _done{0ULL};                                  \
+        int _dev = 0;                                                                        \
+        FEMOL_CUDA_CHECK(cudaGetDevice(&_dev));                                              \
+        const unsigned long long _bit = 1ULL << (_dev & 63);                                 \
+        if (!(_done.load(std::memory_order_acquire) & _bit)) {                               \
+            FEMOL_CUDA_CHECK(cudaFuncSetAttribute(kern, attr, value));                       \
+            _done.fetch_or(_bit, std::memory_order_release);                                 \
+        }                                                                                    \
     } while (0)
 
 #define FEMOL_REQUIRE(cond, msg)                                   \
@@ -162,6 +177,13 @@ static inline int femol_grid_for(int64_t n, int block, int sm_count, int waves =
 }
 
 int femol_sm_count();
+
+// Side stream for work that must not run on the legacy default stream (CUDA-graph capture): one library-owned
+// non-blocking stream per device.  fork: *side waits for everything enqueued on `user` so far; join: `user` waits for
+// everything enqueued on `side`.
+bool femol_stream_is_default(cudaStream_t st);
+int femol_stream_fork(cudaStream_t user, cudaStream_t* side);
+int femol_stream_join(cudaStream_t side, cudaStream_t user);
 
 // ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
 // A CG iteration is ~26 short kernels back to back in one stream (a CUDA graph); the ~1.8 us between the end of one

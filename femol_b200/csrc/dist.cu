@@ -249,7 +249,11 @@ int dpcg_run(femol_plan_t plan, femol_comm* c, int64_t n_owned, const Halo& h, c
         FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
         const double ff = h_sc[D_FF];
         true_rel = ff > 0.0 ? sqrt(h_sc[D_RR] / ff) : 0.0;
-        if (h_sc[D_DONE] == 1.0 || ff == 0.0) { status = FEMOL_OK; break; }
+        if (ff == 0.0) {  // zero right-hand side (global norm): the solution is zero whatever the warm start was
+            FEMOL_CUDA_CHECK(cudaMemsetAsync(u, 0, (size_t)n_local * sizeof(double), st));
+            status = FEMOL_OK; break;
+        }
+        if (h_sc[D_DONE] == 1.0) { status = FEMOL_OK; break; }
         if (restart > 0 && true_rel <= 10.0 * rtol) { status = FEMOL_OK; break; }
         if (restart > 1 && true_rel >= 0.5 * prev_true_rel) { status = FEMOL_S_STAGNATED; break; }
         prev_true_rel = true_rel;

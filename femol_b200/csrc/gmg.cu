@@ -1267,14 +1267,8 @@ extern "C" int femol_gmg_setup(femol_gmg* g, const double* e_base, const double*
     FEMOL_CUDA_CHECK(cudaMemsetAsync(g->coarse_inv, 0, CL.n * CL.n * sizeof(double), st));
     csr_to_dense<<<grid_for(CL.n), 256, 0, st>>>(CL.n, CL.plan->adj_ptr, CL.plan->adj_idx, nd, CL.vals, g->coarse_inv);
     FEMOL_LAUNCH_CHECK();
-    {
-        static bool configured = false;
-        if (!configured) {
-            FEMOL_CUDA_CHECK(cudaFuncSetAttribute(dense_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  GMG_COARSE_MAX_DOF * GMG_COARSE_MAX_DOF * (int)sizeof(double)));
-            configured = true;
-        }
-    }
+    FEMOL_FUNC_ATTR_PER_DEVICE(dense_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               GMG_COARSE_MAX_DOF * GMG_COARSE_MAX_DOF * (int)sizeof(double));
     dense_inverse<<<1, 1024, CL.n * CL.n * sizeof(double), st>>>((int)CL.n, g->coarse_inv);
     FEMOL_LAUNCH_CHECK();
     return FEMOL_OK;

@@ -218,7 +218,11 @@ int pcg_run(femol_plan_t plan, const double* vals, const double* f, double* u, d
         FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
         const double ff = h_sc[S_FF];
         true_rel = ff > 0.0 ? sqrt(h_sc[S_RR] / ff) : 0.0;
-        if (h_sc[S_DONE] == 1.0 || ff == 0.0) { status = FEMOL_OK; break; }
+        if (ff == 0.0) {  // zero right-hand side: the solution is zero whatever the warm start was
+            FEMOL_CUDA_CHECK(cudaMemsetAsync(u, 0, (size_t)n * sizeof(double), st));
+            status = FEMOL_OK; break;
+        }
+        if (h_sc[S_DONE] == 1.0) { status = FEMOL_OK; break; }
         if (restart > 0 && true_rel <= 10.0 * rtol) { status = FEMOL_OK; break; }  // drift within a digit: accept
         // the recurrence converged but the true residual no longer improves: attainable accuracy
         // (~ eps * cond(A)) reached — a direct solver stops at the same level
@@ -444,11 +448,13 @@ extern "C" int64_t femol_pcg_gmg_workspace_doubles(femol_plan_t p) {
     return 4 * p->n_nodes * p->ndof + S_NSLOT + FEMOL_RED_WS_DOUBLES;
 }
 
-extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* vals, const double* f, double* u, double rtol,
-                             int max_iter, double* ws, int* h_iters, double* h_relres, void* stream) {
-    FEMOL_REQUIRE(plan && gmg && vals && f && u && ws, "femol_pcg_gmg: null argument");
-    FEMOL_REQUIRE(rtol > 0.0 && max_iter >= 0, "femol_pcg_gmg: bad tolerance / iteration limit");
-    cudaStream_t st = (cudaStream_t)stream;
+namespace {
+
+std::atomic<long long> g_graph_stats[4];  // captures attempted | captures instantiated | graph launches | solves on the side stream
+
+// The solve proper.  `exec` is owned by the caller (destroyed on every exit path).
+int pcg_gmg_run(femol_plan_t plan, femol_gmg* gmg, const double* vals, const double* f, double* u, double rtol,
+                int max_iter, double* ws, int* h_iters, double* h_relres, cudaStream_t st, cudaGraphExec_t& exec) {
     const int64_t n = plan->n_nodes * plan->ndof;
     GpcgCtx c;
     c.plan = plan; c.gmg = gmg; c.vals = vals; c.u = u; c.n = n;
@@ -462,19 +468,21 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
     double true_rel = 0.0, prev_true_rel = 1e300;
     const int batch = 2;
     const bool use_graph = getenv("FEMOL_NO_GRAPH") == nullptr;
-    cudaGraphExec_t exec = nullptr;
     long long graph_kernels = 0;
-    auto cleanup = [&]() { if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; } };
     for (int restart = 0; restart < 6; ++restart) {
         int rc = femol_apply_launch(plan, vals, u, c.q, nullptr, nullptr, nullptr, st);
-        if (rc != FEMOL_OK) { cleanup(); return rc; }
+        if (rc != FEMOL_OK) return rc;
         gpcg_init<<<c.vgrid, VEC_THREADS, 0, st>>>(n, f, c.q, c.r, c.sc, c.red, rtol, restart);
         FEMOL_LAUNCH_CHECK();
         FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, c.sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
         FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
         const double ff = h_sc[S_FF];
         true_rel = ff > 0.0 ? sqrt(h_sc[S_RR] / ff) : 0.0;
-        if (h_sc[S_DONE] == 1.0 || ff == 0.0) { status = FEMOL_OK; break; }
+        if (ff == 0.0) {  // zero right-hand side: the solution is zero whatever the warm start was
+            FEMOL_CUDA_CHECK(cudaMemsetAsync(u, 0, (size_t)n * sizeof(double), st));
+            status = FEMOL_OK; break;
+        }
+        if (h_sc[S_DONE] == 1.0) { status = FEMOL_OK; break; }
         if (restart > 0 && true_rel <= 10.0 * rtol) { status = FEMOL_OK; break; }
         if (restart > 1 && true_rel >= 0.5 * prev_true_rel) { status = FEMOL_S_STAGNATED; break; }
         prev_true_rel = true_rel;
@@ -482,13 +490,14 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
         // z = V(r), rz, p = z
         bool rz_fused = false;
         rc = femol_gmg_vcycle_internal(gmg, c.r, c.z, st, c.sc + S_RZN, c.red, &rz_fused, false);
-        if (rc != FEMOL_OK) { cleanup(); return rc; }
+        if (rc != FEMOL_OK) return rc;
         if (!rz_fused) gpcg_dot<<<c.vgrid, VEC_THREADS, 0, st>>>(n, c.r, c.z, c.sc, c.red);
         gpcg_direction<<<c.vgrid, VEC_THREADS, 0, st>>>(n, c.z, c.p, c.sc, 1);
         FEMOL_LAUNCH_CHECK();
         if (use_graph && !exec) {  // capture one CG iteration (static launch sequence) once per solve
             cudaGraph_t graph = nullptr;
             const long long before = femol_launch_count(0);
+            g_graph_stats[0].fetch_add(1);
             if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
                 const int crc = gpcg_iteration(c, st);
                 graph_kernels = femol_launch_count(0) - before;
@@ -497,6 +506,7 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
                 if (crc != FEMOL_OK || e != cudaSuccess || !graph ||
                     cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
                 if (graph) cudaGraphDestroy(graph);
+                if (exec) g_graph_stats[1].fetch_add(1);
             }
             cudaGetLastError();  // a failed capture must not poison later launch checks
         }
@@ -510,8 +520,8 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
             first_batch = 0;
             if (nb > max_iter - total_iters) nb = max_iter - total_iters;
             for (int it = 0; it < nb; ++it) {
-                if (exec) { FEMOL_CUDA_CHECK(cudaGraphLaunch(exec, st)); femol_count_launches(graph_kernels); }
-                else if ((rc = gpcg_iteration(c, st)) != FEMOL_OK) { cleanup(); return rc; }
+                if (exec) { FEMOL_CUDA_CHECK(cudaGraphLaunch(exec, st)); femol_count_launches(graph_kernels); g_graph_stats[2].fetch_add(1); }
+                else if ((rc = gpcg_iteration(c, st)) != FEMOL_OK) return rc;
             }
             FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, c.sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
             FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -521,7 +531,6 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
         }
         if (status == FEMOL_S_BREAKDOWN || !finished) break;
     }
-    cleanup();
     femol_gmg_iteration_hint(gmg, total_iters);
     if (status == FEMOL_S_NOT_CONVERGED) {
         int rc = femol_apply_launch(plan, vals, u, c.q, nullptr, nullptr, nullptr, st);
@@ -536,4 +545,41 @@ extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* va
     if (h_iters) *h_iters = total_iters;
     if (h_relres) *h_relres = true_rel;
     return status;
+}
+
+}  // namespace
+
+// [0] graph captures attempted, [1] captures instantiated, [2] graph launches, [3] solves moved to the side stream
+extern "C" int femol_graph_stats(int64_t* out, int reset) {
+    FEMOL_REQUIRE(out, "femol_graph_stats: null argument");
+    for (int i = 0; i < 4; ++i) {
+        out[i] = (int64_t)g_graph_stats[i].load();
+        if (reset) g_graph_stats[i].store(0);
+    }
+    return FEMOL_OK;
+}
+
+extern "C" int femol_pcg_gmg(femol_plan_t plan, femol_gmg* gmg, const double* vals, const double* f, double* u, double rtol,
+                             int max_iter, double* ws, int* h_iters, double* h_relres, void* stream) {
+    FEMOL_REQUIRE(plan && gmg && vals && f && u && ws, "femol_pcg_gmg: null argument");
+    FEMOL_REQUIRE(rtol > 0.0 && max_iter >= 0, "femol_pcg_gmg: bad tolerance / iteration limit");
+    // Stream capture is not permitted on the legacy default stream (what torch hands out unless the caller made a side
+    // stream current): the solve then runs on a library-owned non-blocking stream, ordered after the caller's stream
+    // on entry and joined back into it on exit, so the caller sees ordinary stream semantics.
+    cudaStream_t user = (cudaStream_t)stream, st = user;
+    bool forked = false;
+    if (getenv("FEMOL_NO_GRAPH") == nullptr && femol_stream_is_default(user)) {
+        int rc = femol_stream_fork(user, &st);
+        if (rc != FEMOL_OK) return rc;
+        forked = true;
+        g_graph_stats[3].fetch_add(1);
+    }
+    cudaGraphExec_t exec = nullptr;
+    int rc = pcg_gmg_run(plan, gmg, vals, f, u, rtol, max_iter, ws, h_iters, h_relres, st, exec);
+    if (exec) cudaGraphExecDestroy(exec);
+    if (forked) {
+        const int jrc = femol_stream_join(st, user);
+        if (rc >= 0 && jrc != FEMOL_OK) rc = jrc;
+    }
+    return rc;
 }

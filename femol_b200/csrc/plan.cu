@@ -56,6 +56,53 @@ int femol_sm_count() {
     return cached;
 }
 
+bool femol_stream_is_default(cudaStream_t st) {
+    return st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread;
+}
+
+namespace {
+struct SideStream { cudaStream_t st; cudaEvent_t fork_ev, join_ev; bool ready; };
+SideStream g_side[64];
+std::atomic_flag g_side_lock = ATOMIC_FLAG_INIT;
+}  // namespace
+
+static int side_stream_get(SideStream** out) {
+    int dev = 0;
+    FEMOL_CUDA_CHECK(cudaGetDevice(&dev));
+    SideStream& s = g_side[dev & 63];
+    while (g_side_lock.test_and_set(std::memory_order_acquire)) {}
+    cudaError_t e = cudaSuccess;
+    if (!s.ready) {
+        e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.fork_ev, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.join_ev, cudaEventDisableTiming);
+        s.ready = e == cudaSuccess;
+    }
+    g_side_lock.clear(std::memory_order_release);
+    FEMOL_CUDA_CHECK(e);
+    *out = &s;
+    return FEMOL_OK;
+}
+
+int femol_stream_fork(cudaStream_t user, cudaStream_t* side) {
+    SideStream* s = nullptr;
+    int rc = side_stream_get(&s);
+    if (rc != FEMOL_OK) return rc;
+    FEMOL_CUDA_CHECK(cudaEventRecord(s->fork_ev, user));
+    FEMOL_CUDA_CHECK(cudaStreamWaitEvent(s->st, s->fork_ev, 0));
+    *side = s->st;
+    return FEMOL_OK;
+}
+
+int femol_stream_join(cudaStream_t side, cudaStream_t user) {
+    SideStream* s = nullptr;
+    int rc = side_stream_get(&s);
+    if (rc != FEMOL_OK) return rc;
+    FEMOL_CUDA_CHECK(cudaEventRecord(s->join_ev, side));
+    FEMOL_CUDA_CHECK(cudaStreamWaitEvent(user, s->join_ev, 0));
+    return FEMOL_OK;
+}
+
 namespace {
 
 constexpr int MAX_CAND = 128;  // max distinct nodes adjacent to one node

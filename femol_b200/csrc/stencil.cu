@@ -261,12 +261,8 @@ int launch_stencil_c(femol_plan_t p, const femol_matrix_free* mf, const double* 
     constexpr int TI = 32, TJ = 8, NT = 2, NPT = ND == 2 ? 2 : 1;
     constexpr int WW = (TI + 1) * (TJ + 1);
     constexpr size_t smem = (size_t)NT * ((TJ + 2) * (TI + 2) * ND + WW + (WW & 1)) * sizeof(double);
-    static bool configured = false;
     auto kern = stencil_tile_kernel<ND, COAT, TI, TJ, NT, NPT, MODE>;
-    if (!configured) {
-        FEMOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    FEMOL_FUNC_ATTR_PER_DEVICE(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int tiles_i = (int)((mf->nx + 1 + TI - 1) / TI);
     const int64_t n_tiles = (int64_t)tiles_i * ((mf->ny + 1 + TJ - 1) / TJ);
     const int64_t n_cta = (n_tiles + NT - 1) / NT;

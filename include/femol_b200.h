@@ -178,6 +178,11 @@ int femol_gmg_apply(femol_gmg_t gmg, const double* r, double* z, void* stream); 
 int64_t femol_pcg_gmg_workspace_doubles(femol_plan_t plan);
 int femol_pcg_gmg(femol_plan_t plan, femol_gmg_t gmg, const double* vals, const double* f, double* u, double rtol,
                   int max_iter, double* ws, int* h_iters, double* h_relres, void* stream);
+/* One CG iteration of femol_pcg_gmg is captured into a CUDA graph per solve.  Capture is not permitted on the legacy
+ * default stream, so a solve called with stream 0 runs on a library-owned non-blocking stream that is ordered after
+ * `stream` on entry and joined back on exit.  h_out[0] captures attempted, [1] graphs instantiated, [2] graph
+ * launches, [3] solves moved to the side stream (process totals; reset != 0 clears them). */
+int femol_graph_stats(int64_t* h_out, int reset);
 
 /* ---- multi-GPU row-block partition: distributed block-Jacobi PCG --------------------------------
  * One process per GPU.  `plan` is the plan of the rank's LOCAL mesh: owned nodes first (a contiguous range of the

@@ -270,3 +270,23 @@ LOOKUP_TABLE default
     assert np.allclose(mesh.point_data['Ux'], [0.0, 0.1, 0.2, 0.3, 0.4])
     vals = {k: mesh.cell_data['X'][k][0] for k in mesh.contains}
     assert vals == {'quad': 0.25, 'triangle': 0.75}
+
+
+def test_tracked_force_vector_flags_in_place_edits():
+    """problem.F is handed back as an ndarray subclass whose writes raise a dirty flag (in-place edits of
+    the load vector were silently ignored, then made to raise; now they are picked up by the next assembly)."""
+    from femol_b200.FEM import _TrackedVector as T
+    F = T(np.arange(6.0))
+    assert isinstance(F, np.ndarray) and F.dtype == np.float64 and not F.dirty
+    assert type(F + 1.0) is np.ndarray and type(np.sum(F)) is np.float64 and not F.dirty   # reads do not flag
+    assert float(F @ F) == 55.0 and not F.dirty
+    F[2] = 7.0
+    assert F.dirty and F[2] == 7.0
+    F = T(np.zeros(6)); v = F[1:4]; v[0] = 3.0                     # write through a view
+    assert F.dirty and F[1] == 3.0
+    F = T(np.ones(6)); F *= 2.0                                    # in-place operator keeps the tracked type
+    assert isinstance(F, T) and F.dirty and F[0] == 2.0
+    F = T(np.ones(6)); np.add(F, 1.0, out=F)
+    assert F.dirty and F[5] == 2.0
+    G = np.array(F, dtype=np.float64)                              # private copies are plain arrays
+    assert type(G) is np.ndarray
