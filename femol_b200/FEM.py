@@ -200,6 +200,7 @@ class FEM_Problem(object):
         self._Kv = self._Mv = None
         self._K_host = self._M_host = None
         self._U_dev = None
+        self._U_mask_key = None
         self._X_modal = None  # last eigenvector block (warm start)
         self._epoch = 0
         self._mask_key = None
@@ -210,11 +211,14 @@ class FEM_Problem(object):
         self._F_key = None
         self._F_ref = None
         self._grid_shape = None
+        self._lattice = None
         self._gmg = None
         self._gmg2 = None           # hierarchy of S K S (plates), on a view of the plan
         self._plan_view = None
         self._gmg2_refs = None
         self._gmg_mask_key = None
+        self._gmg_is_lattice = False
+        self._vc_refs = None        # variable-core laminates: (base matrices, coating matrices, 0/1 indicator) on the device
         self._gmg_stale = True
         self._gmg_ws = None
         self._K_scaled = False
@@ -306,6 +310,7 @@ class FEM_Problem(object):
         self._E_host.clear()
         self._F_key = None
         self._grid_shape = None
+        self._lattice = None
         self._gmg_stale = True
         if self._dev is not None:
             self._dev.xy.copy_(torch.from_numpy(np.ascontiguousarray(self.mesh.points[:, :2], dtype=np.float64)))
@@ -470,6 +475,7 @@ class FEM_Problem(object):
                   _lib.ptr(mask), _lib.ptr(xpow), _lib.ptr(vals), _lib.stream())
         self._variable_core = True
         if which == 'K':
+            self._vc_refs = (E[0], E[1], xpow)          # what the lattice multigrid coarsens (xpow = the 0/1 indicator)
             self._Kv, self._K_host, self._gmg_stale, self._K_scaled = vals, None, True, False
             _lib.call('femol_plan_set_matrix_free', d.plan, 0, 0, None, None, None, None, None)
         else:
@@ -551,8 +557,12 @@ class FEM_Problem(object):
         d = self.device
         if self._Kv is None:
             self.assemble('K')
-        if self._U_dev is None or not self.warm_start:
+        # warm start from the previous displacement - unless the Dirichlet set changed since (the old field is not
+        # zero on the newly fixed dofs, and an iterative solve would only drive it there to within its tolerance)
+        self._fixed_mask()
+        if self._U_dev is None or not self.warm_start or self._U_mask_key != self._mask_key:
             self._U_dev = torch.zeros(d.n, dtype=torch.float64, device=d.dev)
+            self._U_mask_key = self._mask_key
         iters = ctypes.c_int(0)
         relres = ctypes.c_double(0.0)
         precond = self._effective_preconditioner()
@@ -601,29 +611,83 @@ class FEM_Problem(object):
             self._grid_shape = shape
         return self._grid_shape or None
 
+    def node_lattice(self):
+        """Lattice description of a mesh whose nodes occupy every point of a uniform (Nx+1) x (Ny+1) lattice exactly
+        once and whose cells (one type: T3, Q4 or T6) each lie inside one cell of the grid over every second lattice
+        line - `rectangle_T3`, `rectangle_T6` (corner + mid-side nodes, Nx = 2 nelx), `rectangle_Q4` in any
+        numbering - or None.  Feeds femol_gmg_create_lattice: dict(Nx, Ny, lat_node, node_lat, child_ptr, child_idx)."""
+        if self._lattice is None:
+            self._lattice = self._find_node_lattice() or False
+        return self._lattice or None
+
+    def _find_node_lattice(self):
+        m = self.mesh
+        if len(m.contains) != 1:
+            return None
+        cells = np.asarray(m.cells[m.contains[0]])
+        if cells.shape[1] not in (3, 4, 6) or m.N_nodes >= 2 ** 31:
+            return None
+        idx = []
+        for c in (m.points[:, 0], m.points[:, 1]):
+            lo, hi = float(c.min()), float(c.max())
+            if not hi > lo:
+                return None
+            srt = np.sort(c)
+            lines = srt[np.concatenate([[True], np.diff(srt) > 1e-9 * (hi - lo)])]
+            n = lines.shape[0] - 1
+            if n < 1 or not np.allclose(np.diff(lines), (hi - lo) / n, rtol=1e-6, atol=0):
+                return None
+            k = np.rint((c - lo) / ((hi - lo) / n)).astype(np.int64)
+            if np.abs(lo + k * ((hi - lo) / n) - c).max() > 1e-6 * (hi - lo) / n:
+                return None
+            idx.append((k, n))
+        (li, Nx), (lj, Ny) = idx
+        if (Nx + 1) * (Ny + 1) != m.N_nodes:
+            return None
+        lat = lj * (Nx + 1) + li
+        if np.bincount(lat, minlength=m.N_nodes).max() != 1:
+            return None
+        ci, cj = li[cells], lj[cells]
+        I, J = ci.min(axis=1) // 2, cj.min(axis=1) // 2
+        if (ci.max(axis=1) > 2 * I + 2).any() or (cj.max(axis=1) > 2 * J + 2).any():
+            return None                                  # a cell straddles two coarse cells
+        nxc, nyc = (Nx + 1) // 2, (Ny + 1) // 2
+        parent = I * nyc + J
+        order = np.argsort(parent, kind='stable')        # ascending element id inside a parent: deterministic sums
+        ptr = np.concatenate([[0], np.cumsum(np.bincount(parent, minlength=nxc * nyc))])
+        lat_node = np.empty(m.N_nodes, dtype=np.int32)
+        lat_node[lat] = np.arange(m.N_nodes, dtype=np.int32)
+        return {'Nx': int(Nx), 'Ny': int(Ny), 'lat_node': lat_node, 'node_lat': lat.astype(np.int32),
+                'child_ptr': ptr.astype(np.int32), 'child_idx': order.astype(np.int32)}
+
     def _effective_preconditioner(self):
         p = self.preconditioner
-        if self._variable_core:
-            return 'block_jacobi' if p in ('auto', 'gmg') else p    # per-element matrices: no shared-Ke hierarchy
+        # per-element matrices (variable-core laminates, T3 / T6 meshes) have no shared-Ke hierarchy: they take the
+        # lattice hierarchy when the nodes form a lattice
+        shared = bool(self.structured_grid_shape()) and not self._variable_core
         if p == 'auto':
-            shape = self.structured_grid_shape()
-            return 'gmg' if (shape and self.mesh.N_ele >= 64) else 'block_jacobi'
-        if p == 'gmg' and not self.structured_grid_shape():
-            raise _lib.FemolError("preconditioner='gmg' needs a rectangle_Q4-ordered structured mesh")
+            ok = self.mesh.N_ele >= 64 and (shared or self.node_lattice() is not None)
+            return 'gmg' if ok else 'block_jacobi'
+        if p == 'gmg' and not shared and self.node_lattice() is None:
+            raise _lib.FemolError("preconditioner='gmg' needs a mesh whose nodes form a lattice (rectangle_Q4 / T3 / T6)")
         return p
 
     def _gmg_ready(self):
         """Create (once per Dirichlet set) and refresh (once per assembled K) the multigrid hierarchy."""
         d = self.device
         mask = self._fixed_mask()
+        lattice = self._variable_core or not self.structured_grid_shape()
+        if lattice:
+            return self._gmg_ready_lattice(mask)
         hourglass = self._hourglass_enabled()
-        if self._gmg is None or self._gmg_mask_key != self._mask_key or hourglass != (self._gmg2 is not None):
+        if (self._gmg is None or self._gmg_mask_key != self._mask_key or hourglass != (self._gmg2 is not None)
+                or self._gmg_is_lattice):
             self._destroy_gmg()
             nx, ny = self.structured_grid_shape()
             handle = ctypes.c_void_p()
             _lib.call('femol_gmg_create', nx, ny, self.N_dof, d.plan, _lib.ptr(mask), int(self.gmg_smoothing_steps),
                       float(self.gmg_omega), _lib.stream(), ctypes.byref(handle))
-            self._gmg, self._gmg_mask_key, self._gmg_stale = handle, self._mask_key, True
+            self._gmg, self._gmg_mask_key, self._gmg_stale, self._gmg_is_lattice = handle, self._mask_key, True, False
             if hourglass:
                 view, h2 = ctypes.c_void_p(), ctypes.c_void_p()
                 _lib.call('femol_plan_create_view', d.plan, ctypes.byref(view))
@@ -652,6 +716,35 @@ class FEM_Problem(object):
                           hc.ctypes.data if hc is not None else None, xp, _lib.ptr(mask), _lib.ptr(self._Kv))
                 _lib.call('femol_gmg_setup', self._gmg2, _lib.ptr(Ebh), _lib.ptr(Ech), xp, _lib.ptr(self._Kv), _lib.stream())
                 self._gmg2_refs = (Ebh, Ech, mask)
+            self._gmg_stale = False
+        return self._gmg
+
+    def _gmg_ready_lattice(self, mask):
+        """Lattice hierarchy (femol_gmg_create_lattice): level 0 = the assembled operator of this mesh, element
+        matrices shared or one per element (T3 / T6 meshes, variable-core laminates)."""
+        d = self.device
+        if self._gmg is None or self._gmg_mask_key != self._mask_key or not self._gmg_is_lattice:
+            self._destroy_gmg()
+            lat = self.node_lattice()
+            dev = {k: torch.from_numpy(lat[k]).to(d.dev) for k in ('lat_node', 'node_lat', 'child_ptr', 'child_idx')}
+            handle = ctypes.c_void_p()
+            _lib.call('femol_gmg_create_lattice', lat['Nx'], lat['Ny'], self.N_dof, d.plan, _lib.ptr(mask),
+                      _lib.ptr(dev['lat_node']), _lib.ptr(dev['node_lat']), _lib.ptr(dev['child_ptr']),
+                      _lib.ptr(dev['child_idx']), int(self.gmg_smoothing_steps), float(self.gmg_omega), _lib.stream(),
+                      ctypes.byref(handle))
+            torch.cuda.current_stream().synchronize()      # the library copies the index arrays in stream order
+            self._gmg, self._gmg_mask_key, self._gmg_stale, self._gmg_is_lattice = handle, self._mask_key, True, True
+        if self._gmg_stale:
+            if self._variable_core:
+                Eb, Ec, xp_t = self._vc_refs
+                pe_b = pe_c = 1
+                xp = _lib.ptr(xp_t)
+            else:
+                Eb, pe_b = self._element_matrices('K', False)
+                Ec, pe_c = self._element_matrices('K', True) if self.coating else (None, 0)
+                xp = _lib.ptr(d.xpow) if self._K_scaled else None
+            _lib.call('femol_gmg_setup_lattice', self._gmg, _lib.ptr(Eb), pe_b, _lib.ptr(Ec), pe_c, xp, _lib.ptr(self._Kv),
+                      _lib.stream())
             self._gmg_stale = False
         return self._gmg
 

@@ -40,6 +40,7 @@ struct Level {
     double* dinv;       // [n_nodes][ND][ND]
     double *r, *e, *t;  // work vectors (level 0: r, e supplied by the caller through vcycle)
     double *r2, *e2;    // second coarse visit of the F / W cycle (levels >= 1)
+    int32_t* lat_node;  // level 0 of a lattice hierarchy: lattice index (x-fastest) -> node id; NULL = identity
 };
 
 }  // namespace
@@ -62,6 +63,12 @@ struct femol_gmg {
     int cycle_depth;     // coarse levels 1 .. cycle_depth get the second visit, deeper ones a plain V-cycle
     femol_gmg* mod;      // hierarchy of the sign-modulated operator S K S (femol_gmg_attach_modulated) or NULL
     double *mod_r, *mod_z;  // S r and the correction of that hierarchy
+    // lattice hierarchy (femol_gmg_create_lattice): level 0 is ANY mesh whose nodes form a complete lattice
+    // (T3 / T6 / Q4 in any node numbering); level 1 is the Q4 grid over every second lattice line
+    bool lattice;
+    int32_t* node_lat;   // [n_nodes] lattice index of every level-0 node
+    int32_t* child_ptr;  // [n_elem(level 1) + 1] level-0 elements inside each level-1 element ...
+    int32_t* child_idx;  // ... ascending (deterministic summation order)
 };
 
 namespace {
@@ -87,12 +94,13 @@ __global__ void make_conn(int64_t nx, int64_t ny, int32_t* __restrict__ conn) {
 }
 
 __global__ void coarsen_mask(int64_t nxf, int64_t nyf, const uint8_t* __restrict__ ff, int64_t nxc, int64_t nyc,
-                             uint8_t* __restrict__ fc) {
+                             uint8_t* __restrict__ fc, const int32_t* __restrict__ lat_node) {
     const int64_t nn = (nxc + 1) * (nyc + 1);
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nn; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t J = t / (nxc + 1), I = t - J * (nxc + 1);
         const int64_t i = min(2 * I, nxf), j = min(2 * J, nyf);
-        fc[t] = ff ? ff[j * (nxf + 1) + i] : 0;
+        const int64_t lat = j * (nxf + 1) + i;
+        fc[t] = ff ? ff[lat_node ? lat_node[lat] : lat] : 0;
     }
 }
 
@@ -292,6 +300,81 @@ coarsen_elements_fast(int nxf, int nyf, int nxc, int nyc, const double* __restri
     }
 }
 
+// Lattice hierarchy, level 0 -> 1: the children of a coarse Q4 element are the level-0 elements (NN nodes each: T3,
+// Q4, T6) that lie inside it; P_c holds the bilinear weights of the child's nodes, taken from their lattice
+// coordinates.  One warp per coarse element; child matrix (density-scaled, Dirichlet rows / columns zeroed) and weights
+// staged in shared memory; children are visited in ascending element order (deterministic).
+template <int ND, int NN>
+__global__ void __launch_bounds__(128)
+coarsen_lattice(int nxf, int nyf, int nxc, int nyc, const int32_t* __restrict__ conn, const int32_t* __restrict__ node_lat,
+                const int32_t* __restrict__ child_ptr, const int32_t* __restrict__ child_idx,
+                const double* __restrict__ e_base, int base_pe, const double* __restrict__ e_coat, int coat_pe,
+                const double* __restrict__ xpow, const uint8_t* __restrict__ fixed_f, double* __restrict__ out) {
+    constexpr int S = 4 * ND, S2 = S * S, SC = NN * ND, SC2 = SC * SC;
+    constexpr int NE = (S2 + 31) / 32;
+    __shared__ double s_child[4][SC2];
+    __shared__ double s_w[4][NN][4];
+    __shared__ uint32_t s_fm[4][NN];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nec = nxc * nyc;
+    for (int E = blockIdx.x * 4 + wid; E < nec; E += gridDim.x * 4) {
+        const int I = E / nyc, J = E - I * nyc;
+        const double sx = (2 * I + 1 < nxf) ? 0.5 : 1.0, sy = (2 * J + 1 < nyf) ? 0.5 : 1.0;   // trailing single-cell parent
+        double acc[NE];
+#pragma unroll
+        for (int m = 0; m < NE; ++m) acc[m] = 0.0;
+        for (int k = child_ptr[E]; k < child_ptr[E + 1]; ++k) {
+            const int e = child_idx[k];
+            __syncwarp();
+            if (lane < NN) {
+                const int node = conn[(size_t)e * NN + lane];
+                const int lat = node_lat[node];
+                const int j = lat / (nxf + 1), i = lat - j * (nxf + 1);
+                const double ps = (i - 2 * I) * sx, pt = (j - 2 * J) * sy;
+                s_w[wid][lane][0] = (1 - ps) * (1 - pt); s_w[wid][lane][1] = ps * (1 - pt);
+                s_w[wid][lane][2] = ps * pt; s_w[wid][lane][3] = (1 - ps) * pt;
+                s_fm[wid][lane] = fixed_f ? fixed_f[node] : 0u;
+            }
+            __syncwarp();
+            const double w = xpow ? xpow[e] : 1.0;
+            const double* kb = e_base + (base_pe ? (size_t)e * SC2 : 0);
+            const double* kc = e_coat ? e_coat + (coat_pe ? (size_t)e * SC2 : 0) : nullptr;
+            for (int idx = lane; idx < SC2; idx += 32) {
+                const int r = idx / SC, c = idx - r * SC;
+                double v = kc ? kb[idx] + w * kc[idx] : w * kb[idx];
+                if (((s_fm[wid][r / ND] >> (r % ND)) | (s_fm[wid][c / ND] >> (c % ND))) & 1u) v = 0.0;
+                s_child[wid][idx] = v;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < NE; ++m) {
+                const int idx = lane + 32 * m;
+                if (idx < S2) {
+                    const int r = idx / S, cc = idx - r * S;
+                    const int p = r / ND, da = r - p * ND, q = cc / ND, db = cc - q * ND;
+                    double v = 0.0;
+                    for (int a = 0; a < NN; ++a) {
+                        const double wa = s_w[wid][a][p];
+                        if (wa != 0.0) {
+                            double t = 0.0;
+#pragma unroll
+                            for (int b = 0; b < NN; ++b) t += s_w[wid][b][q] * s_child[wid][(a * ND + da) * SC + b * ND + db];
+                            v += wa * t;
+                        }
+                    }
+                    acc[m] += v;
+                }
+            }
+        }
+        double* o = out + (size_t)E * S2;
+#pragma unroll
+        for (int m = 0; m < NE; ++m) {
+            const int idx = lane + 32 * m;
+            if (idx < S2) o[idx] = acc[m];
+        }
+    }
+}
+
 // ---- transfer operators ---------------------------------------------------------------------------------------
 // 1-D weight of fine node c + dc in the restriction onto the coarse node centred at fine index c (n fine cells):
 // the transpose of cmap1d.  c is even except for the last node of an odd grid, which has no half-weight neighbours.
@@ -310,7 +393,8 @@ template <int ND>
 __global__ void __launch_bounds__(256)
 restrict_kernel(int64_t nxf64, int64_t nyf64, int64_t nxc64, int64_t nyc64, const uint8_t* __restrict__ ff,
                 const uint8_t* __restrict__ fc, const double* __restrict__ rf, double* __restrict__ rc,
-                const double* __restrict__ dinv_c, double omega, double* __restrict__ ec) {
+                const double* __restrict__ dinv_c, double omega, double* __restrict__ ec,
+                const int32_t* __restrict__ lat_node) {
     FEMOL_PDL_SYNC();
     const int nxf = (int)nxf64, nyf = (int)nyf64, nxc = (int)nxc64, nyc = (int)nyc64;
     const int nn = (nxc + 1) * (nyc + 1);
@@ -327,7 +411,8 @@ restrict_kernel(int64_t nxf64, int64_t nyf64, int64_t nxc64, int64_t nyc64, cons
             for (int di = -1; di <= 1; ++di) {
                 const double w = wy * rweight1d(ic, di, nxf);
                 if (w == 0.0) continue;
-                const int nf = (jc + dj) * (nxf + 1) + ic + di;
+                const int lat = (jc + dj) * (nxf + 1) + ic + di;
+                const int nf = lat_node ? __ldg(&lat_node[lat]) : lat;    // lattice hierarchy: permuted fine level
                 const uint32_t fm = ff ? __ldg(&ff[nf]) : 0u;
 #pragma unroll
                 for (int d = 0; d < ND; d += 2) {
@@ -366,12 +451,13 @@ restrict_kernel(int64_t nxf64, int64_t nyf64, int64_t nxc64, int64_t nyc64, cons
 template <int ND>
 __global__ void __launch_bounds__(256)
 prolong_add_kernel(int64_t nxf64, int64_t nyf64, int64_t nxc64, const uint8_t* __restrict__ ff,
-                   const double* __restrict__ ec, const double* ef, double* out) {
+                   const double* __restrict__ ec, const double* ef, double* out, const int32_t* __restrict__ lat_node) {
     FEMOL_PDL_SYNC();
     const int nxf = (int)nxf64, nyf = (int)nyf64, nxc = (int)nxc64;
     const int nn = (nxf + 1) * (nyf + 1);
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += gridDim.x * blockDim.x) {
-        const int j = t / (nxf + 1), i = t - j * (nxf + 1);
+    for (int lat = blockIdx.x * blockDim.x + threadIdx.x; lat < nn; lat += gridDim.x * blockDim.x) {
+        const int j = lat / (nxf + 1), i = lat - j * (nxf + 1);
+        const int t = lat_node ? __ldg(&lat_node[lat]) : lat;             // node id (lattice hierarchy: permuted)
         int64_t I0, I1, J0, J1; double u0, u1, v0, v1;
         cmap1d(i, nxf, I0, u0, I1, u1);      // I1 = I0 (weight 0) when the node coincides with a coarse node
         cmap1d(j, nyf, J0, v0, J1, v1);
@@ -982,7 +1068,8 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, boo
         const bool coarse_regular = l + 1 != g->n_levels - 1;   // every smoothing level starts from omega Dinv r
         FEMOL_CUDA_CHECK(femol_launch_pdl(restrict_kernel<ND>, dim3(grid_for(C.n_nodes)), dim3(256), 0, st, L.nx, L.ny, C.nx, C.ny,
                                           (const uint8_t*)L.fixed, (const uint8_t*)C.fixed, (const double*)L.t, C.r,
-                                          (const double*)(coarse_regular ? C.dinv : nullptr), g->omega, C.e));
+                                          (const double*)(coarse_regular ? C.dinv : nullptr), g->omega, C.e,
+                                          (const int32_t*)L.lat_node));
         femol_count_launch();
         rc = vcycle<ND>(g, l + 1, C.r, C.e, st, coarse_regular, nullptr, nullptr, nullptr, cyc);
         if (rc != FEMOL_OK) return rc;
@@ -999,7 +1086,8 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, boo
         }
         if (femol_apply_has_jacobi(L.plan, L.vals)) {
             FEMOL_CUDA_CHECK(femol_launch_pdl(prolong_add_kernel<ND>, dim3(grid_for(L.n_nodes)), dim3(256), 0, st, L.nx, L.ny, C.nx,
-                                              (const uint8_t*)L.fixed, (const double*)C.e, (const double*)e, L.t));
+                                              (const uint8_t*)L.fixed, (const double*)C.e, (const double*)e, L.t,
+                                              (const int32_t*)L.lat_node));
             femol_count_launch();
             // level 0 inside CG: the last kernel of the V-cycle also delivers r . z
             const femol_epilogue jac = {FEMOL_EPI_JACOBI, r, L.dinv, g->omega, rz_out, red_ws};
@@ -1007,7 +1095,7 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, boo
             return L.vals32 ? femol_spmv_f32_epilogue_launch(L.plan, L.vals32, L.t, e, jac, st)
                             : femol_apply_epilogue_launch(L.plan, L.vals, L.t, e, jac, st);
         }
-        prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e, e);
+        prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e, e, L.lat_node);
         FEMOL_LAUNCH_CHECK();
         return smooth<ND>(g, l, r, e, false, st);
     }
@@ -1017,11 +1105,11 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, boo
     if (rc != FEMOL_OK) return rc;
     residual_kernel<<<grid_for(L.n), 256, 0, st>>>(L.n, r, L.t, L.t);
     FEMOL_LAUNCH_CHECK();
-    restrict_kernel<ND><<<grid_for(C.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, C.ny, L.fixed, C.fixed, L.t, C.r, nullptr, 0.0, nullptr);
+    restrict_kernel<ND><<<grid_for(C.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, C.ny, L.fixed, C.fixed, L.t, C.r, nullptr, 0.0, nullptr, L.lat_node);
     FEMOL_LAUNCH_CHECK();
     rc = vcycle<ND>(g, l + 1, C.r, C.e, st);
     if (rc != FEMOL_OK) return rc;
-    prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e, e);
+    prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e, e, L.lat_node);
     FEMOL_LAUNCH_CHECK();
     return smooth<ND>(g, l, r, e, false, st);
 }
@@ -1097,9 +1185,16 @@ extern "C" int femol_gmg_destroy(femol_gmg* g) {
     cudaFree(g->child_g);
     cudaFree(g->d_desc);
     cudaFree(g->mod_r); cudaFree(g->mod_z);
+    cudaFree(g->lv[0].lat_node); cudaFree(g->node_lat); cudaFree(g->child_ptr); cudaFree(g->child_idx);
     delete g;
     return FEMOL_OK;
 }
+
+namespace {
+struct LatticeArgs { const int32_t *lat_node, *node_lat, *child_ptr, *child_idx; };
+int gmg_create_impl(int64_t nx, int64_t ny, int ndof, femol_plan_t fine_plan, const uint8_t* fine_fixed, int nu, double omega,
+                    const LatticeArgs* lat, cudaStream_t st, femol_gmg** out);
+}  // namespace
 
 extern "C" int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t fine_plan, const uint8_t* fine_fixed,
                                 int nu, double omega, void* stream, femol_gmg** out) {
@@ -1107,7 +1202,30 @@ extern "C" int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t f
     FEMOL_REQUIRE(ndof == 2 || ndof == 6, "femol_gmg_create: ndof must be 2 or 6");
     FEMOL_REQUIRE(fine_plan->nn == 4 && fine_plan->ndof == ndof && fine_plan->n_elem == nx * ny &&
                   fine_plan->n_nodes == (nx + 1) * (ny + 1), "femol_gmg_create: plan is not an nx x ny structured Q4 mesh");
-    cudaStream_t st = (cudaStream_t)stream;
+    return gmg_create_impl(nx, ny, ndof, fine_plan, fine_fixed, nu, omega, nullptr, (cudaStream_t)stream, out);
+}
+
+// Lattice hierarchy: the fine mesh is ANY single-cell-type mesh (T3, Q4, T6; any node / element numbering) whose nodes
+// occupy every point of an (Nx + 1) x (Ny + 1) lattice exactly once and whose elements each lie inside one cell of the
+// coarse grid over every second lattice line.  lat_node [(Nx+1)(Ny+1)]: lattice index (x-fastest) -> node; node_lat
+// [n_nodes]: its inverse; child_ptr [NEc + 1] / child_idx [n_elem]: the fine elements inside each coarse element
+// (NEc = ceil(Nx/2) ceil(Ny/2), coarse elements numbered I * ceil(Ny/2) + J), ascending.  Device arrays, copied.
+extern "C" int femol_gmg_create_lattice(int64_t Nx, int64_t Ny, int ndof, femol_plan_t fine_plan, const uint8_t* fine_fixed,
+                                        const int32_t* lat_node, const int32_t* node_lat, const int32_t* child_ptr,
+                                        const int32_t* child_idx, int nu, double omega, void* stream, femol_gmg** out) {
+    FEMOL_REQUIRE(out && fine_plan && Nx >= 1 && Ny >= 1 && lat_node && node_lat && child_ptr && child_idx,
+                  "femol_gmg_create_lattice: bad argument");
+    FEMOL_REQUIRE(ndof == 2 || ndof == 6, "femol_gmg_create_lattice: ndof must be 2 or 6");
+    FEMOL_REQUIRE((fine_plan->nn == 3 || fine_plan->nn == 4 || fine_plan->nn == 6) && fine_plan->ndof == ndof &&
+                  fine_plan->n_nodes == (Nx + 1) * (Ny + 1) && fine_plan->n_nodes < (1LL << 31),
+                  "femol_gmg_create_lattice: the plan's nodes do not fill an (Nx+1) x (Ny+1) lattice");
+    const LatticeArgs lat = {lat_node, node_lat, child_ptr, child_idx};
+    return gmg_create_impl(Nx, Ny, ndof, fine_plan, fine_fixed, nu, omega, &lat, (cudaStream_t)stream, out);
+}
+
+namespace {
+int gmg_create_impl(int64_t nx, int64_t ny, int ndof, femol_plan_t fine_plan, const uint8_t* fine_fixed, int nu, double omega,
+                    const LatticeArgs* lat, cudaStream_t st, femol_gmg** out) {
     femol_gmg* g = new femol_gmg();
     memset(g, 0, sizeof(*g));
     g->nd = ndof; g->nu = nu > 0 ? nu : 2; g->omega = omega > 0 ? omega : 0.6;
@@ -1136,6 +1254,18 @@ extern "C" int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t f
         if (l == 0) {
             L.plan = fine_plan;
             L.fixed = const_cast<uint8_t*>(fine_fixed);
+            if (lat) {
+                const int64_t nec = coarse_of(cx) * coarse_of(cy);
+                g->lattice = true;
+                GCHECK(cudaMalloc(&L.lat_node, L.n_nodes * sizeof(int32_t)));
+                GCHECK(cudaMalloc(&g->node_lat, L.n_nodes * sizeof(int32_t)));
+                GCHECK(cudaMalloc(&g->child_ptr, (nec + 1) * sizeof(int32_t)));
+                GCHECK(cudaMalloc(&g->child_idx, fine_plan->n_elem * sizeof(int32_t)));
+                GCHECK(cudaMemcpyAsync(L.lat_node, lat->lat_node, L.n_nodes * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+                GCHECK(cudaMemcpyAsync(g->node_lat, lat->node_lat, L.n_nodes * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+                GCHECK(cudaMemcpyAsync(g->child_ptr, lat->child_ptr, (nec + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+                GCHECK(cudaMemcpyAsync(g->child_idx, lat->child_idx, fine_plan->n_elem * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+            }
         } else {
             Level& F = g->lv[l - 1];
             int32_t* conn = nullptr;
@@ -1145,7 +1275,7 @@ extern "C" int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t f
             cudaFree(conn);
             if (rc != FEMOL_OK) return fail(rc);
             GCHECK(cudaMalloc(&L.fixed, L.n_nodes));
-            coarsen_mask<<<grid_for(L.n_nodes), 256, 0, st>>>(F.nx, F.ny, F.fixed, cx, cy, L.fixed);
+            coarsen_mask<<<grid_for(L.n_nodes), 256, 0, st>>>(F.nx, F.ny, F.fixed, cx, cy, L.fixed, F.lat_node);
             GCHECK(cudaGetLastError());
             GCHECK(cudaMalloc(&L.ke, L.n_elem * S2 * sizeof(double)));
             GCHECK(cudaMalloc(&L.vals, L.plan->nnz * sizeof(double)));
@@ -1222,12 +1352,43 @@ extern "C" int femol_gmg_create(int64_t nx, int64_t ny, int ndof, femol_plan_t f
     *out = g;
     return FEMOL_OK;
 }
+}  // namespace
 
 // (Re)build the hierarchy for the current densities: called once per assembled fine matrix.
+namespace {
+int gmg_setup_impl(femol_gmg* g, const double* e_base, int base_pe, const double* e_coat, int coat_pe, const double* xpow,
+                   const double* fine_vals, cudaStream_t st);
+}  // namespace
+
 extern "C" int femol_gmg_setup(femol_gmg* g, const double* e_base, const double* e_coat, const double* xpow,
                                const double* fine_vals, void* stream) {
     FEMOL_REQUIRE(g && e_base && fine_vals, "femol_gmg_setup: null argument");
-    cudaStream_t st = (cudaStream_t)stream;
+    FEMOL_REQUIRE(!g->lattice, "femol_gmg_setup: lattice hierarchies are refreshed with femol_gmg_setup_lattice");
+    return gmg_setup_impl(g, e_base, 0, e_coat, 0, xpow, fine_vals, (cudaStream_t)stream);
+}
+
+// Lattice hierarchy: element matrices of the FINE mesh, shared (pe = 0: one S x S matrix) or one per element (pe = 1,
+// the reference's unstructured path FEM.py:608-695), base [+ coating]; child = xpow_e * base, or base + xpow_e * coat.
+extern "C" int femol_gmg_setup_lattice(femol_gmg* g, const double* e_base, int base_pe, const double* e_coat, int coat_pe,
+                                       const double* xpow, const double* fine_vals, void* stream) {
+    FEMOL_REQUIRE(g && e_base && fine_vals, "femol_gmg_setup_lattice: null argument");
+    FEMOL_REQUIRE(g->lattice, "femol_gmg_setup_lattice: not a lattice hierarchy");
+    return gmg_setup_impl(g, e_base, base_pe, e_coat, coat_pe, xpow, fine_vals, (cudaStream_t)stream);
+}
+
+namespace {
+template <int ND, int NN>
+void launch_coarsen_lattice(femol_gmg* g, int blocks, const double* e_base, int base_pe, const double* e_coat, int coat_pe,
+                            const double* xpow, cudaStream_t st) {
+    Level& F = g->lv[0];
+    Level& C = g->lv[1];
+    coarsen_lattice<ND, NN><<<blocks, 128, 0, st>>>((int)F.nx, (int)F.ny, (int)C.nx, (int)C.ny, F.plan->conn, g->node_lat,
+                                                    g->child_ptr, g->child_idx, e_base, base_pe, e_coat, coat_pe, xpow,
+                                                    F.fixed, C.ke);
+}
+
+int gmg_setup_impl(femol_gmg* g, const double* e_base, int base_pe, const double* e_coat, int coat_pe, const double* xpow,
+                   const double* fine_vals, cudaStream_t st) {
     const int nd = g->nd;
     g->lv[0].vals = const_cast<double*>(fine_vals);
     const char* env_old = getenv("FEMOL_GMG_OLD_COARSEN");
@@ -1238,7 +1399,13 @@ extern "C" int femol_gmg_setup(femol_gmg* g, const double* e_base, const double*
         int64_t blocks = (C.n_elem + 3) / 4;
         const int64_t cap = (int64_t)femol_sm_count() * 16;
         if (blocks > cap) blocks = cap;
-        if (nd == 2) {
+        if (l == 1 && g->lattice) {
+            const int nn = F.plan->nn;
+#define LAT_CASE(ND, NN) \
+            if (nd == ND && nn == NN) launch_coarsen_lattice<ND, NN>(g, (int)blocks, e_base, base_pe, e_coat, coat_pe, xpow, st);
+            LAT_CASE(2, 3) LAT_CASE(2, 4) LAT_CASE(2, 6) LAT_CASE(6, 3) LAT_CASE(6, 4) LAT_CASE(6, 6)
+#undef LAT_CASE
+        } else if (nd == 2) {
             if (l == 1) {
                 child_images<2><<<2, 256, 0, st>>>(e_base, e_coat, g->child_g);
                 coarsen_elements<2, true><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, nullptr, e_base, e_coat, xpow, F.fixed, g->child_g, C.ke);
@@ -1273,6 +1440,7 @@ extern "C" int femol_gmg_setup(femol_gmg* g, const double* e_base, const double*
     FEMOL_LAUNCH_CHECK();
     return FEMOL_OK;
 }
+}  // namespace
 
 extern "C" int femol_gmg_info(femol_gmg* g, int64_t* h_info /* [0]=levels, then (nx, ny) per level */) {
     FEMOL_REQUIRE(g && h_info, "femol_gmg_info: null argument");

@@ -164,6 +164,22 @@ int femol_gmg_setup(femol_gmg_t gmg, const double* e_base, const double* e_coat,
                     const double* fine_vals, void* stream);
 int femol_gmg_info(femol_gmg_t gmg, int64_t* h_info);
 
+/* Lattice hierarchy: the same multigrid for ANY single-cell-type fine mesh (T3, T6, Q4 in any node / element
+ * numbering; the reference's unstructured assembly path FEM.py:608-695) whose nodes occupy every point of an
+ * (Nx+1) x (Ny+1) lattice exactly once - rectangle_T3 (lattice = corner nodes) and rectangle_T6 (corner + mid-side
+ * nodes: Nx = 2 nelx) - and whose elements each lie inside one cell of the coarse grid over every second lattice line.
+ * Level 0 is the assembled operator of that mesh (block-Jacobi smoothing on the CSR values); level 1 is the bilinear Q4
+ * grid ceil(Nx/2) x ceil(Ny/2), its element matrices the Galerkin images of the fine elements inside each coarse
+ * element; the levels below are those of femol_gmg_create.  Device int32 arrays (copied): lat_node [(Nx+1)(Ny+1)]
+ * lattice index (x-fastest) -> node, node_lat [n_nodes] its inverse, child_ptr [NEc+1] / child_idx [n_elem] the fine
+ * elements inside coarse element I * ceil(Ny/2) + J, ascending.  femol_gmg_setup_lattice takes the fine element
+ * matrices, shared (pe = 0) or one per element (pe = 1); femol_pcg_gmg / femol_gmg_apply work unchanged. */
+int femol_gmg_create_lattice(int64_t Nx, int64_t Ny, int ndof, femol_plan_t fine_plan, const uint8_t* fine_fixed,
+                             const int32_t* lat_node, const int32_t* node_lat, const int32_t* child_ptr,
+                             const int32_t* child_idx, int nu, double omega, void* stream, femol_gmg_t* out);
+int femol_gmg_setup_lattice(femol_gmg_t gmg, const double* e_base, int base_pe, const double* e_coat, int coat_pe,
+                            const double* xpow, const double* fine_vals, void* stream);
+
 /* Hourglass correction for the reference's Q4 Mindlin plate (shear integrated with one point, elements.py:1029-1054):
  * its assembled operator has a family of low-energy modes w = (-1)^(i+j) x smooth envelope that are only restrained
  * through the boundary conditions (plates with free edges), invisible to the smoother and to bilinear coarse grids;

@@ -648,6 +648,152 @@ def test_gmg_vcycle_is_symmetric_positive(F):
     assert info[0] >= 3 and (info[1], info[2]) == (37, 19) and (info[3], info[4]) == (19, 10)
 
 
+def _lattice_problem(F, kind, nx, ny, model='plane', seed=5):
+    Lx, Ly = float(nx), float(ny)
+    if kind == 'Q4perm':
+        # a rectangle_Q4 mesh renumbered at random: nodes still fill a lattice, but nothing is x-fastest any more
+        m0 = F.mesh.rectangle_Q4(Lx, Ly, nx, ny)
+        rng = np.random.default_rng(seed)
+        perm = rng.permutation(m0.N_nodes)                 # new id of old node k
+        pts = np.empty_like(m0.points); pts[perm] = m0.points
+        cells = perm[m0.cells['quad']][rng.permutation(m0.N_ele)]
+        mesh = F.Mesh(pts, {'quad': cells}, quad_element=F.elements.Q4)
+    else:
+        mesh = {'T3': F.mesh.rectangle_T3, 'T6': F.mesh.rectangle_T6}[kind](Lx, Ly, nx, ny)
+    p = F.FEM_Problem('displacement', model, mesh)
+    if model == 'plane':
+        p.define_materials(F.materials.general_isotropic()); p.define_tensors(1)
+        p.add_fixed_domain(F.domains.inside_box([0], [[0, Ly]]), ddls=[0, 1])
+        p.add_forces([0, -1.0], F.domains.inside_box([Lx], [[0, Ly]]))
+    else:
+        p.define_materials(F.materials.IsotropicMaterial(10920, 0.3, 1)); p.define_tensors(0.5)
+        p.add_fixed_domain(F.domains.inside_box([0], [[0, Ly]]))
+        p.add_forces([0, 0, -1e-2, 0, 0, 0], F.domains.inside_box([Lx], [[0, Ly]]))
+    x = cases.density_field(mesh.N_ele, seed=seed + 1)
+    return p, x
+
+
+@pytest.mark.parametrize('kind,nx,ny,model', [('T6', 24, 12, 'plane'), ('T6', 17, 9, 'plane'), ('T3', 40, 20, 'plane'),
+                                              ('T3', 33, 15, 'plane'), ('Q4perm', 31, 16, 'plane'), ('T6', 10, 6, 'plate'),
+                                              ('Q4perm', 12, 9, 'plate')])
+def test_lattice_gmg_on_triangle_and_renumbered_meshes(F, kind, nx, ny, model):
+    """Lattice hierarchy (femol_gmg_create_lattice): level 0 is the assembled operator of a T3 / T6 mesh or of a Q4
+    mesh in arbitrary numbering, coarse levels are bilinear Q4 grids.  Same solution as block-Jacobi PCG and scipy,
+    in far fewer iterations; 'auto' selects it."""
+    import scipy.sparse.linalg as sla
+    p, x = _lattice_problem(F, kind, nx, ny, model)
+    ctype = p.mesh.contains[0]
+    assert p.structured_grid_shape() is None and p.node_lattice() is not None
+    assert p._effective_preconditioner() == 'gmg'
+    p.solver_rtol = 1e-9 if model == 'plane' else 1e-7
+    p.assemble('K', X={ctype: x}, p=3)
+    p.preconditioner = 'block_jacobi'
+    U_bj = p.solve_device().cpu().numpy().copy()
+    it_bj = p.solver_info['iterations']
+    p.preconditioner = 'auto'
+    p._U_dev = None
+    U_mg = p.solve_device().cpu().numpy().copy()
+    info = dict(p.solver_info)
+    assert info['converged'] and info['preconditioner'] == 'gmg', info
+    assert info['iterations'] < (max(70, it_bj // 4) if model == 'plane' else it_bj // 2), (info, it_bj)
+    U_ref = sla.spsolve(p.K.tocsc(), p.F)
+    c_ref = p.F @ U_ref
+    assert abs(p.F @ U_mg - c_ref) / abs(c_ref) < 1e-6 and abs(p.F @ U_bj - c_ref) / abs(c_ref) < 1e-6
+    assert rel(U_mg, U_ref) < 1e-4, (rel(U_mg, U_ref), info)
+    # the hierarchy: lattice on level 0, every second lattice line below
+    info64 = (ctypes.c_int64 * 64)()
+    F._lib.call('femol_gmg_info', p._gmg, info64)
+    lat = p.node_lattice()
+    assert (info64[1], info64[2]) == (lat['Nx'], lat['Ny']) and (info64[3], info64[4]) == ((lat['Nx'] + 1) // 2, (lat['Ny'] + 1) // 2)
+
+
+def test_lattice_vcycle_is_symmetric_positive_and_level1_is_galerkin(F):
+    """The lattice V-cycle is a symmetric positive operator, and its level-1 operator is exactly P^T K P with the
+    bilinear lattice interpolation (checked through the two-level identity on a T6 mesh)."""
+    import torch
+    p, x = _lattice_problem(F, 'T6', 12, 7)
+    p.assemble('K', X={'triangle': x}, p=3)
+    g = p._gmg_ready()
+    d = p.device
+    rng = np.random.default_rng(0)
+    fixed = p.fixed_dofs()
+    R = rng.standard_normal((3, d.n)); R[:, fixed] = 0
+    Z = []
+    for r in R:
+        rd = torch.from_numpy(r).cuda(); zd = torch.empty_like(rd)
+        F._lib.call('femol_gmg_apply', g, rd.data_ptr(), zd.data_ptr(), F._lib.stream())
+        Z.append(zd.cpu().numpy())
+    assert abs(R[0] @ Z[1] - R[1] @ Z[0]) < 1e-10 * abs(R[0] @ Z[1]) + 1e-14 * np.linalg.norm(Z[0]) * np.linalg.norm(R[1])
+    assert all(R[i] @ Z[i] > 0 for i in range(3))
+    # the same cycle in numpy with Galerkin operators P^T K P on every level must give the same z
+    import scipy.sparse as sp
+    K = p.K.tocsr()
+    lat = p.node_lattice()
+    z_ref = _numpy_lattice_vcycle(K, lat, fixed, R[0], p.gmg_omega)
+    # 1e-6: the coarse levels' smoother products read single-precision copies of the operators (FEMOL_GMG_F32)
+    assert rel(Z[0], z_ref) < 1e-6, rel(Z[0], z_ref)
+
+
+def _numpy_lattice_vcycle(K, lat, fixed_dofs, r, omega, nd=2):
+    """V(1,1) cycle with damped block-Jacobi on Galerkin operators; the numpy statement of gmg.cu for a lattice mesh."""
+    import scipy.sparse as sp
+
+    def p1(n):
+        nc = (n + 1) // 2
+        P = np.zeros((n + 1, nc + 1))
+        for i in range(n + 1):
+            if i % 2 == 0: P[i, i // 2] = 1
+            elif i == n: P[i, (i + 1) // 2] = 1
+            else: P[i, i // 2] = .5; P[i, i // 2 + 1] = .5
+        return sp.csr_matrix(P)
+
+    def dinv(A):
+        n = A.shape[0] // nd
+        B = A.tobsr(blocksize=(nd, nd)); B.sort_indices()
+        D = np.zeros((n, nd, nd))
+        for i in range(n):
+            for k in range(B.indptr[i], B.indptr[i + 1]):
+                if B.indices[k] == i: D[i] = B.data[k]
+        return np.linalg.inv(D)
+
+    def jac(A, D, rr, e):
+        res = rr if e is None else rr - A @ e
+        dz = omega * np.einsum('nab,nb->na', D, res.reshape(-1, nd)).reshape(-1)
+        return dz if e is None else e + dz
+
+    levels = []
+    A, Nx, Ny, perm = K, lat['Nx'], lat['Ny'], lat['node_lat']
+    fx = np.zeros(K.shape[0], bool); fx[fixed_dofs] = True
+    while True:
+        if A.shape[0] <= 100 or (Nx == 1 and Ny == 1):
+            levels.append((A, None, None)); break
+        P2 = sp.kron(p1(Ny), p1(Nx)).tocsr()
+        if perm is not None:
+            P2 = P2[perm]
+        P = sp.diags((~fx).astype(float)) @ sp.kron(P2, sp.identity(nd)).tocsr()
+        nxc, nyc = (Nx + 1) // 2, (Ny + 1) // 2
+        I, J = np.meshgrid(np.arange(nxc + 1), np.arange(nyc + 1))
+        fl = (np.minimum(2 * J, Ny) * (Nx + 1) + np.minimum(2 * I, Nx)).reshape(-1)
+        if perm is not None:
+            inv = np.empty_like(perm); inv[perm] = np.arange(perm.shape[0]); fl = inv[fl]
+        fc = fx.reshape(-1, nd)[fl].reshape(-1)
+        keep = sp.diags((~fc).astype(float))
+        P = P @ keep
+        Ac = (P.T @ A @ P + sp.diags(fc.astype(float))).tocsr()
+        levels.append((A, dinv(A), P))
+        A, Nx, Ny, perm, fx = Ac, nxc, nyc, None, fc
+
+    def cyc(l, rr):
+        A, D, P = levels[l]
+        if P is None:
+            # the device inverse decouples dead coarse dofs; none here
+            return np.linalg.solve(A.toarray(), rr)
+        e = jac(A, D, rr, None)
+        e = e + P @ cyc(l + 1, P.T @ (rr - A @ e))
+        return jac(A, D, rr, e)
+    return cyc(0, r)
+
+
 def test_gmg_rejects_unstructured(F):
     p = cases.build_problem(F, cases.CASES['comp_q4_jitter_10x5'])
     p.preconditioner = 'gmg'
