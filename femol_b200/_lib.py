@@ -62,6 +62,13 @@ SIGNATURES = {
     'femol_pcg_dist_workspace_doubles': (c_i64, [P, c_i64]),
     'femol_pcg_dist': (c_int, [P, P, c_i64, c_int, P, P, P, P, P, P, P, P, c_dbl, c_int, c_int, P,
                        ctypes.POINTER(c_int), ctypes.POINTER(c_dbl), P]),
+    'femol_gmg_truncate': (c_int, [P, c_int]),
+    'femol_gmg_set_dist': (c_int, [P, P, c_int, P, P, P, P, P, P, P, P]),
+    'femol_gmg_dist_refresh': (c_int, [P, P]),
+    'femol_gmg_dist_exchange': (c_int, [P, c_int, P, c_int, P]),
+    'femol_dist_allreduce_sum': (c_int, [P, P, c_i64, P]),
+    'femol_pcg_gmg_dist_workspace_doubles': (c_i64, [P]),
+    'femol_pcg_gmg_dist': (c_int, [P, P, P, P, P, c_dbl, c_int, P, ctypes.POINTER(c_int), ctypes.POINTER(c_dbl), P]),
     'femol_spmm': (c_int, [P, P, P, c_int, P, c_int, c_int, P]),
     'femol_gram_workspace_doubles': (c_i64, [c_int, c_int]),
     'femol_gram': (c_int, [c_i64, c_int, c_int, P, c_int, P, c_int, P, P, P]),

@@ -16,6 +16,7 @@
 #include <string.h>
 #include "common.cuh"
 #include "spmv.cuh"
+#include "dist.cuh"
 
 extern "C" int femol_precond_setup(femol_plan_t p, const double* vals, int kind, double* dinv, void* stream);
 
@@ -343,4 +344,243 @@ extern "C" int femol_pcg_dist(femol_plan_t plan, femol_comm* comm, int64_t n_own
     if (plan->ndof == 6) return dpcg_run<6>(plan, comm, n_owned_nodes, h, vals, f, u, rtol, max_iter, precond, ws, h_iters, h_relres, st);
     femol_set_error("femol_pcg_dist: unsupported ndof %d", plan->ndof);
     return FEMOL_E_ARG;
+}
+
+// =====================================================================================================================
+// Strip-distributed multigrid PCG (gmg.cu: "Strip-distributed hierarchy").  Transport = NCCL: a halo exchange is one
+// grouped ncclSend/ncclRecv pair per neighbour on contiguous row slices (local vectors are x-fastest lattice rows, so
+// nothing is packed); reductions are ncclAllReduce on device scalars, in stream.
+// =====================================================================================================================
+int femol_comm_rank(const femol_comm* c) { return c->rank; }
+int femol_comm_size(const femol_comm* c) { return c->nranks; }
+
+int femol_dist_exchange(femol_comm* c, double* x, int width, const femol_strip& s, cudaStream_t st) {
+    if (c->nranks == 1) return FEMOL_OK;
+    const int64_t rowd = s.row_nodes * width;
+    const bool lower = c->rank > 0, upper = c->rank < c->nranks - 1;
+    NCCL_CHECK(g_nccl.GroupStart());
+    if (lower) {
+        NCCL_CHECK(g_nccl.Send(x + s.own_lo * rowd, (size_t)(s.h_down * rowd), ncclDouble_, c->rank - 1, c->comm, st));
+        NCCL_CHECK(g_nccl.Recv(x + (s.own_lo - s.h_up) * rowd, (size_t)(s.h_up * rowd), ncclDouble_, c->rank - 1, c->comm, st));
+    }
+    if (upper) {
+        NCCL_CHECK(g_nccl.Send(x + (s.own_hi - s.h_up) * rowd, (size_t)(s.h_up * rowd), ncclDouble_, c->rank + 1, c->comm, st));
+        NCCL_CHECK(g_nccl.Recv(x + s.own_hi * rowd, (size_t)(s.h_down * rowd), ncclDouble_, c->rank + 1, c->comm, st));
+    }
+    NCCL_CHECK(g_nccl.GroupEnd());
+    return FEMOL_OK;
+}
+
+int femol_dist_allreduce(femol_comm* c, double* buf, int64_t count, cudaStream_t st) {
+    if (c->nranks == 1 || count == 0) return FEMOL_OK;
+    NCCL_CHECK(g_nccl.AllReduce(buf, buf, (size_t)count, ncclDouble_, ncclSum_, c->comm, st));
+    return FEMOL_OK;
+}
+
+extern "C" int femol_dist_allreduce_sum(femol_comm* c, double* buf, int64_t count, void* stream) {
+    FEMOL_REQUIRE(c && buf && count >= 0, "femol_dist_allreduce_sum: bad argument");
+    return femol_dist_allreduce(c, buf, count, (cudaStream_t)stream);
+}
+
+namespace {
+
+// scalar slots of the distributed multigrid PCG (device)
+enum { G_RZN = 0, G_RZO = 1, G_PQ = 2, G_RR = 3, G_FF = 4, G_DONE = 5, G_ITER = 6, G_TOL2 = 7, G_L0 = 8, G_L1 = 9, G_NSLOT = 16 };
+
+// r = f - q on the owned range ; local (r.r, f.f) -> sc[G_L0..1]
+__global__ void __launch_bounds__(DT)
+dg_init(int64_t n, const double* __restrict__ f, const double* __restrict__ q, double* __restrict__ r, double* __restrict__ sc,
+        double* __restrict__ red) {
+    __shared__ double s_red[32 * 2];
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double fv = f[i], rv = fv - q[i];
+        r[i] = rv;
+        acc[0] += rv * rv; acc[1] += fv * fv;
+    }
+    grid_sum_finish<2>(acc, red, red_ticket(red), sc + G_L0, s_red);
+}
+
+__global__ void dg_init_finalize(double* sc, double rtol, int restart) {
+    sc[G_RR] = sc[G_L0]; sc[G_FF] = sc[G_L1];
+    sc[G_TOL2] = rtol * rtol * sc[G_L1];
+    if (!restart) sc[G_ITER] = 0.0;
+    sc[G_DONE] = (sc[G_L0] <= rtol * rtol * sc[G_L1]) ? 1.0 : 0.0;
+}
+
+// sc[slot] = a . b over the owned range (local part)
+__global__ void __launch_bounds__(DT)
+dg_dot(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, double* __restrict__ red) {
+    FEMOL_PDL_SYNC();
+    __shared__ double s_red[32];
+    double acc[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc[0] += a[i] * b[i];
+    grid_sum_finish<1>(acc, red, red_ticket(red), out, s_red);
+}
+
+// u += alpha p ; r -= alpha q ; local r.r -> sc[G_L1] ; z = omega Dinv r (the V-cycle's first sweep), owned nodes
+template <int ND>
+__global__ void __launch_bounds__(DT)
+dg_update(int64_t n_nodes, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ u, double* __restrict__ r,
+          double* __restrict__ sc, double* __restrict__ red, const double* __restrict__ dinv, double omega, double* __restrict__ z) {
+    __shared__ double s_red[32];
+    const bool done = sc[G_DONE] != 0.0;
+    const double alpha = done ? 0.0 : sc[G_RZN] / sc[G_PQ];
+    double acc[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+        double rv[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const int64_t o = i * ND + d;
+            if (!done) u[o] += alpha * p[o];
+            rv[d] = r[o] - alpha * q[o];
+            if (!done) r[o] = rv[d];
+            acc[0] += rv[d] * rv[d];
+        }
+        if (!done && dinv) {
+            const double* B = dinv + i * ND * ND;
+#pragma unroll
+            for (int a = 0; a < ND; ++a) {
+                double s = 0.0;
+#pragma unroll
+                for (int b = 0; b < ND; ++b) s += __ldg(&B[a * ND + b]) * rv[b];
+                z[i * ND + a] = omega * s;
+            }
+        }
+    }
+    // every rank takes part in the reduction that follows, converged or not
+    grid_sum_finish<1>(acc, red, red_ticket(red), sc + G_L1, s_red);
+}
+
+// after the all-reduce of (r.z, r.r): rotate the r.z slots, count the iteration, test convergence
+__global__ void dg_iter_finalize(double* sc, int first) {
+    if (sc[G_DONE] != 0.0) return;
+    sc[G_RZO] = sc[G_RZN];
+    sc[G_RZN] = sc[G_L0];
+    if (first) return;
+    sc[G_RR] = sc[G_L1];
+    sc[G_ITER] += 1.0;
+    const double pq = sc[G_PQ];
+    if (!(pq > 0.0) || !(sc[G_L1] == sc[G_L1])) sc[G_DONE] = 2.0;
+    else if (sc[G_L1] <= sc[G_TOL2]) sc[G_DONE] = 1.0;
+}
+
+// first: p = z ; else p = z + (rz_new / rz_old) p     (owned range)
+__global__ void __launch_bounds__(DT)
+dg_direction(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ sc, int first) {
+    if (sc[G_DONE] != 0.0) return;
+    const double beta = first ? 0.0 : sc[G_RZN] / sc[G_RZO];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = first ? z[i] : z[i] + beta * p[i];
+}
+
+}  // namespace
+
+bool femol_gmg_first_sweep(femol_gmg* g, const double** dinv, double* omega);
+int femol_gmg_iteration_hint(femol_gmg* g, int set);
+
+extern "C" int64_t femol_pcg_gmg_dist_workspace_doubles(femol_plan_t p) {
+    if (!p) return 0;
+    return 4 * p->n_nodes * p->ndof + G_NSLOT + FEMOL_RED_WS_DOUBLES;
+}
+
+// K u = f on the strip partition with the distributed V-cycle as preconditioner.  plan / vals / f / u are the LOCAL
+// arrays of the rank's strip (all local rows; u and the result are valid on owned rows, ghost rows of u are refreshed).
+extern "C" int femol_pcg_gmg_dist(femol_plan_t plan, femol_gmg* gmg, const double* vals, const double* f, double* u, double rtol,
+                                  int max_iter, double* ws, int* h_iters, double* h_relres, void* stream) {
+    FEMOL_REQUIRE(plan && gmg && vals && f && u && ws, "femol_pcg_gmg_dist: null argument");
+    FEMOL_REQUIRE(rtol > 0.0 && max_iter >= 0, "femol_pcg_gmg_dist: bad tolerance / iteration limit");
+    FEMOL_REQUIRE(femol_gmg_is_dist(gmg), "femol_pcg_gmg_dist: the hierarchy is not distributed (femol_gmg_set_dist)");
+    FEMOL_REQUIRE(plan->ndof == 2 || plan->ndof == 6, "femol_pcg_gmg_dist: ndof must be 2 or 6");
+    cudaStream_t st = (cudaStream_t)stream;
+    femol_comm* c = femol_gmg_dist_comm(gmg);
+    const femol_strip s = *femol_gmg_dist_strip(gmg, 0);
+    const int nd = plan->ndof;
+    FEMOL_REQUIRE(s.row_nodes * s.n_rows == plan->n_nodes, "femol_pcg_gmg_dist: plan and strip disagree");
+    const int64_t n = plan->n_nodes * nd;
+    const int64_t off = s.own_lo * s.row_nodes * nd;                 // first owned entry
+    const int64_t n_own_nodes = (s.own_hi - s.own_lo) * s.row_nodes;
+    const int64_t n_own = n_own_nodes * nd;
+    double* r = ws; double* p = r + n; double* q = p + n; double* z = q + n; double* sc = z + n; double* red = sc + G_NSLOT;
+    const int vgrid = femol_grid_for(n_own, DT, plan->sm_count, 8);
+    const int ngrid = femol_grid_for(n_own_nodes, DT, plan->sm_count, 8);
+    const double* dinv0 = nullptr; double omega0 = 0.0;
+    const bool first_sweep = femol_gmg_first_sweep(gmg, &dinv0, &omega0);
+    FEMOL_CUDA_CHECK(cudaMemsetAsync(ws, 0, (size_t)(4 * n + G_NSLOT + FEMOL_RED_WS_DOUBLES) * sizeof(double), st));
+    double h_sc[G_NSLOT];
+    int total_iters = 0, status = FEMOL_S_NOT_CONVERGED, rc;
+    double true_rel = 0.0, prev_true_rel = 1e300;
+    const int batch = 4;
+    auto true_residual = [&](int restart) -> int {
+        if ((rc = femol_dist_exchange(c, u, nd, s, st)) != FEMOL_OK) return rc;
+        if ((rc = femol_apply_launch(plan, vals, u, q, nullptr, nullptr, nullptr, st)) != FEMOL_OK) return rc;
+        dg_init<<<vgrid, DT, 0, st>>>(n_own, f + off, q + off, r + off, sc, red);
+        FEMOL_LAUNCH_CHECK();
+        if ((rc = femol_dist_allreduce(c, sc + G_L0, 2, st)) != FEMOL_OK) return rc;
+        dg_init_finalize<<<1, 1, 0, st>>>(sc, rtol, restart);
+        FEMOL_LAUNCH_CHECK();
+        FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+        FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
+        true_rel = h_sc[G_FF] > 0.0 ? sqrt(h_sc[G_RR] / h_sc[G_FF]) : 0.0;
+        return FEMOL_OK;
+    };
+    auto rz_and_direction = [&](int first) -> int {
+        dg_dot<<<vgrid, DT, 0, st>>>(n_own, r + off, z + off, sc + G_L0, red);
+        FEMOL_LAUNCH_CHECK();
+        if ((rc = femol_dist_allreduce(c, sc + G_L0, 2, st)) != FEMOL_OK) return rc;
+        dg_iter_finalize<<<1, 1, 0, st>>>(sc, first);
+        dg_direction<<<vgrid, DT, 0, st>>>(n_own, z + off, p + off, sc, first);
+        FEMOL_LAUNCH_CHECK();
+        return FEMOL_OK;
+    };
+    for (int restart = 0; restart < 6; ++restart) {
+        if ((rc = true_residual(restart)) != FEMOL_OK) return rc;
+        if (h_sc[G_FF] == 0.0) {  // zero right-hand side (global norm): the solution is zero whatever the warm start was
+            FEMOL_CUDA_CHECK(cudaMemsetAsync(u, 0, (size_t)n * sizeof(double), st));
+            status = FEMOL_OK; break;
+        }
+        if (h_sc[G_DONE] == 1.0) { status = FEMOL_OK; break; }
+        if (restart > 0 && true_rel <= 10.0 * rtol) { status = FEMOL_OK; break; }
+        if (restart > 1 && true_rel >= 0.5 * prev_true_rel) { status = FEMOL_S_STAGNATED; break; }
+        prev_true_rel = true_rel;
+        if (total_iters >= max_iter) break;
+        if ((rc = femol_gmg_dist_vcycle(gmg, r, z, st, false)) != FEMOL_OK) return rc;
+        if ((rc = rz_and_direction(1)) != FEMOL_OK) return rc;
+        bool finished = false;
+        int first_batch = restart == 0 ? femol_gmg_iteration_hint(gmg, -1) - 3 : batch;
+        while (!finished && total_iters < max_iter) {
+            int nb = first_batch > batch ? first_batch : batch;
+            first_batch = 0;
+            if (nb > max_iter - total_iters) nb = max_iter - total_iters;
+            for (int it = 0; it < nb; ++it) {      // every rank enqueues the same sequence, converged or not
+                if ((rc = femol_dist_exchange(c, p, nd, s, st)) != FEMOL_OK) return rc;
+                if ((rc = femol_apply_launch(plan, vals, p, q, nullptr, nullptr, nullptr, st)) != FEMOL_OK) return rc;
+                dg_dot<<<vgrid, DT, 0, st>>>(n_own, p + off, q + off, sc + G_PQ, red);
+                FEMOL_LAUNCH_CHECK();
+                if ((rc = femol_dist_allreduce(c, sc + G_PQ, 1, st)) != FEMOL_OK) return rc;
+                const double* dv = first_sweep ? dinv0 + s.own_lo * s.row_nodes * nd * nd : nullptr;
+                if (nd == 2) dg_update<2><<<ngrid, DT, 0, st>>>(n_own_nodes, p + off, q + off, u + off, r + off, sc, red, dv, omega0, z + off);
+                else dg_update<6><<<ngrid, DT, 0, st>>>(n_own_nodes, p + off, q + off, u + off, r + off, sc, red, dv, omega0, z + off);
+                FEMOL_LAUNCH_CHECK();
+                if ((rc = femol_gmg_dist_vcycle(gmg, r, z, st, first_sweep)) != FEMOL_OK) return rc;
+                if ((rc = rz_and_direction(0)) != FEMOL_OK) return rc;
+            }
+            FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+            FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
+            total_iters = (int)h_sc[G_ITER];
+            if (h_sc[G_DONE] == 2.0) { status = FEMOL_S_BREAKDOWN; finished = true; }
+            else if (h_sc[G_DONE] == 1.0) finished = true;
+        }
+        if (status == FEMOL_S_BREAKDOWN || !finished) break;
+    }
+    femol_gmg_iteration_hint(gmg, total_iters);
+    if (status == FEMOL_S_NOT_CONVERGED) {
+        if ((rc = true_residual(1)) != FEMOL_OK) return rc;
+        if (true_rel <= 10.0 * rtol) status = FEMOL_OK;
+    }
+    // the caller's sensitivities read u on the ghost rows of its elements
+    if ((rc = femol_dist_exchange(c, u, nd, s, st)) != FEMOL_OK) return rc;
+    if (h_iters) *h_iters = total_iters;
+    if (h_relres) *h_relres = true_rel;
+    return status;
 }

@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "spmv.cuh"
+#include "dist.cuh"
 
 extern "C" int femol_precond_setup(femol_plan_t p, const double* vals, int kind, double* dinv, void* stream);
 
@@ -41,6 +42,21 @@ struct Level {
     double *r, *e, *t;  // work vectors (level 0: r, e supplied by the caller through vcycle)
     double *r2, *e2;    // second coarse visit of the F / W cycle (levels >= 1)
     int32_t* lat_node;  // level 0 of a lattice hierarchy: lattice index (x-fastest) -> node id; NULL = identity
+};
+
+// Strip-distributed hierarchy (femol_gmg_set_dist): levels 0 .. n_dist-1 live on the rank's strip of lattice rows and
+// exchange halo rows with the two neighbours; level n_dist is gathered and handled, together with everything below it,
+// by `coarse`, a hierarchy every rank holds for the whole (small) level-n_dist grid.
+struct GmgDist {
+    femol_comm* comm;
+    int n_dist;
+    femol_strip strip[GMG_MAX_LEVELS];
+    femol_gmg* coarse;            // borrowed
+    femol_plan* coarse_plan;      // borrowed: plan of the global level-n_dist Q4 grid (level 0 of `coarse`)
+    const uint8_t* coarse_fixed;  // borrowed: node mask of that grid
+    int64_t g_nx, g_ny;           // elements of the global level-n_dist grid
+    double *gke, *gvals;          // its element matrices (gathered) and assembled CSR values
+    double *gr, *ge;              // gathered residual / correction
 };
 
 }  // namespace
@@ -69,6 +85,8 @@ struct femol_gmg {
     int32_t* node_lat;   // [n_nodes] lattice index of every level-0 node
     int32_t* child_ptr;  // [n_elem(level 1) + 1] level-0 elements inside each level-1 element ...
     int32_t* child_idx;  // ... ascending (deterministic summation order)
+    bool capped;         // femol_gmg_truncate: the last level is a gather level without coarsest-level solve
+    GmgDist* dist;       // strip-distributed hierarchy or NULL
 };
 
 namespace {
@@ -1151,6 +1169,8 @@ int femol_gmg_iteration_hint(femol_gmg* g, int set) {
 int femol_gmg_vcycle_internal(femol_gmg* g, const double* r, double* z, cudaStream_t st, double* rz_out, double* red_ws,
                               bool* rz_fused, bool presmoothed) {
     if (rz_fused) *rz_fused = false;
+    if (g->dist) return femol_gmg_dist_vcycle(g, r, z, st, presmoothed);
+    if (g->capped) { femol_set_error("femol_gmg: a truncated hierarchy needs femol_gmg_set_dist"); return FEMOL_E_ARG; }
     if (g->mod) {
         // z = V(r) + S V_h(S r): the second cycle works on the sign-modulated operator S K S, whose smooth functions
         // are the hourglass (checkerboard x smooth envelope) functions of K - the low-energy family of the
@@ -1186,6 +1206,10 @@ extern "C" int femol_gmg_destroy(femol_gmg* g) {
     cudaFree(g->d_desc);
     cudaFree(g->mod_r); cudaFree(g->mod_z);
     cudaFree(g->lv[0].lat_node); cudaFree(g->node_lat); cudaFree(g->child_ptr); cudaFree(g->child_idx);
+    if (g->dist) {
+        cudaFree(g->dist->gke); cudaFree(g->dist->gvals); cudaFree(g->dist->gr); cudaFree(g->dist->ge);
+        delete g->dist;
+    }
     delete g;
     return FEMOL_OK;
 }
@@ -1419,6 +1443,7 @@ int gmg_setup_impl(femol_gmg* g, const double* e_base, int base_pe, const double
             else coarsen_elements<6, false><<<(int)blocks, 128, 0, st>>>(F.nx, F.ny, C.nx, C.ny, F.ke, nullptr, nullptr, nullptr, F.fixed, nullptr, C.ke);
         }
         FEMOL_LAUNCH_CHECK();
+        if (g->capped && l == g->n_levels - 1) break;   // gather level: only its element matrices are needed
         int rc = femol_assemble(C.plan, C.ke, 1, nullptr, 0, nullptr, 1.0, C.fixed, nullptr, C.vals, st);
         if (rc != FEMOL_OK) return rc;
         if (C.vals32) {
@@ -1430,6 +1455,7 @@ int gmg_setup_impl(femol_gmg* g, const double* e_base, int base_pe, const double
         int rc = femol_precond_setup(g->lv[l].plan, g->lv[l].vals, FEMOL_PRECOND_BLOCK_JACOBI, g->lv[l].dinv, st);
         if (rc != FEMOL_OK) return rc;
     }
+    if (g->capped) return FEMOL_OK;
     Level& CL = g->lv[g->n_levels - 1];
     FEMOL_CUDA_CHECK(cudaMemsetAsync(g->coarse_inv, 0, CL.n * CL.n * sizeof(double), st));
     csr_to_dense<<<grid_for(CL.n), 256, 0, st>>>(CL.n, CL.plan->adj_ptr, CL.plan->adj_idx, nd, CL.vals, g->coarse_inv);
@@ -1453,4 +1479,182 @@ extern "C" int femol_gmg_info(femol_gmg* g, int64_t* h_info /* [0]=levels, then 
 extern "C" int femol_gmg_apply(femol_gmg* g, const double* r, double* z, void* stream) {
     FEMOL_REQUIRE(g && r && z, "femol_gmg_apply: null argument");
     return femol_gmg_vcycle_internal(g, r, z, (cudaStream_t)stream, nullptr, nullptr, nullptr, false);
+}
+
+// =====================================================================================================================
+// Strip-distributed hierarchy (one large problem partitioned over the GPUs of a box).
+//
+// Every rank builds an ORDINARY hierarchy on its strip of lattice rows (femol_gmg_create / _create_lattice on the local
+// mesh, truncated to n_dist + 1 levels): the partition cuts are multiples of 2^n_dist lattice rows and a strip starts
+// 2^n_dist rows below its first owned row, so the local grids coarsen exactly like the global grid and every local
+// element matrix of every level IS the global one (Galerkin sums of local children: no communication in the set-up of
+// the distributed levels).  Assembled rows are complete for owned nodes only; a V-cycle therefore exchanges the halo
+// rows of a vector before every operator that reads neighbours (4 per level: before the residual product, before the
+// restriction, before the prolongation, before the post-smoothing product).  Level n_dist is small: its residual is
+// gathered (owned rows, all-reduce of a zero-padded vector) and every rank runs the remaining levels redundantly on the
+// whole grid with `coarse`, an ordinary single-GPU hierarchy whose level 0 carries one element matrix per element (the
+// gathered Galerkin matrices of level n_dist) - no latency-bound halo traffic on the small levels.
+// =====================================================================================================================
+bool femol_gmg_is_dist(const femol_gmg* g) { return g && g->dist; }
+const femol_strip* femol_gmg_dist_strip(const femol_gmg* g, int level) { return &g->dist->strip[level]; }
+femol_comm* femol_gmg_dist_comm(const femol_gmg* g) { return g->dist->comm; }
+
+// Keep the first n_levels levels; the last one becomes a gather level (element matrices only).
+extern "C" int femol_gmg_truncate(femol_gmg* g, int n_levels) {
+    FEMOL_REQUIRE(g && n_levels >= 2 && n_levels <= g->n_levels, "femol_gmg_truncate: bad level count");
+    FEMOL_REQUIRE(g->nu == 1 && !g->mod, "femol_gmg_truncate: needs nu = 1 and no attached hierarchy");
+    for (int l = n_levels; l < g->n_levels; ++l) {
+        Level& L = g->lv[l];
+        femol_plan_destroy(L.plan);
+        cudaFree(L.fixed); cudaFree(L.ke); cudaFree(L.vals); cudaFree(L.vals32); cudaFree(L.r); cudaFree(L.e); cudaFree(L.r2); cudaFree(L.e2);
+        cudaFree(L.dinv); cudaFree(L.t);
+        memset(&L, 0, sizeof(L));
+    }
+    g->n_levels = n_levels;
+    g->capped = true;
+    g->fused_from = g->cluster_from = g->solo_from = n_levels;
+    cudaFree(g->coarse_inv); g->coarse_inv = nullptr;
+    return FEMOL_OK;
+}
+
+// h_row0 / h_own_begin / h_own_end: per level 0 .. n_dist, GLOBAL row index of the local grid's first row and of the
+// owned row range [begin, end); h_up / h_down per level.  `coarse` = lattice hierarchy (Q4 cells, identity numbering)
+// over the global level-n_dist grid with plan `coarse_plan` and node mask `coarse_fixed` (device); all borrowed.
+extern "C" int femol_gmg_set_dist(femol_gmg* g, femol_comm* comm, int n_dist, const int64_t* h_row0, const int64_t* h_own_begin,
+                                  const int64_t* h_own_end, const int* h_up, const int* h_down, femol_gmg* coarse,
+                                  femol_plan_t coarse_plan, const uint8_t* coarse_fixed) {
+    FEMOL_REQUIRE(g && comm && coarse && coarse_plan && h_row0 && h_own_begin && h_own_end && h_up && h_down,
+                  "femol_gmg_set_dist: null argument");
+    FEMOL_REQUIRE(g->capped && n_dist == g->n_levels - 1 && !g->dist, "femol_gmg_set_dist: truncate the hierarchy to n_dist + 1 levels first");
+    FEMOL_REQUIRE(coarse->lattice && coarse->nd == g->nd && !coarse->capped && coarse_plan->nn == 4,
+                  "femol_gmg_set_dist: `coarse` must be a complete Q4 lattice hierarchy of the same ndof");
+    GmgDist* d = new GmgDist();
+    memset(d, 0, sizeof(*d));
+    d->comm = comm; d->n_dist = n_dist; d->coarse = coarse; d->coarse_plan = coarse_plan; d->coarse_fixed = coarse_fixed;
+    for (int l = 0; l <= n_dist; ++l) {
+        const Level& L = g->lv[l];
+        femol_strip& s = d->strip[l];
+        s.row_nodes = L.nx + 1; s.n_rows = L.ny + 1; s.row0 = h_row0[l];
+        s.own_lo = h_own_begin[l] - h_row0[l]; s.own_hi = h_own_end[l] - h_row0[l];
+        s.h_up = h_up[l]; s.h_down = h_down[l];
+        const bool ok = s.own_lo >= 0 && s.own_hi > s.own_lo && s.own_hi <= s.n_rows &&
+                        (femol_comm_rank(comm) == 0 || s.own_lo >= s.h_up) &&
+                        (femol_comm_rank(comm) == femol_comm_size(comm) - 1 || s.own_hi + s.h_down <= s.n_rows) &&
+                        s.own_hi - s.own_lo >= (s.h_up > s.h_down ? s.h_up : s.h_down);
+        if (!ok) { delete d; femol_set_error("femol_gmg_set_dist: inconsistent strip at level %d", l); return FEMOL_E_ARG; }
+    }
+    const Level& G = g->lv[n_dist];
+    d->g_nx = coarse->lv[0].nx; d->g_ny = coarse->lv[0].ny;
+    if (d->g_nx != G.nx || d->strip[n_dist].row0 + G.ny > d->g_ny || coarse_plan->n_elem != d->g_nx * d->g_ny) {
+        delete d; femol_set_error("femol_gmg_set_dist: the coarse grid does not match level %d of the strip", n_dist); return FEMOL_E_ARG;
+    }
+    const int S2 = 16 * g->nd * g->nd;
+    const int64_t gn = coarse->lv[0].n;
+    if (cudaMalloc(&d->gke, (size_t)d->g_nx * d->g_ny * S2 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&d->gvals, (size_t)coarse_plan->nnz * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&d->gr, (size_t)gn * sizeof(double)) != cudaSuccess || cudaMalloc(&d->ge, (size_t)gn * sizeof(double)) != cudaSuccess) {
+        cudaFree(d->gke); cudaFree(d->gvals); cudaFree(d->gr); cudaFree(d->ge); delete d;
+        femol_set_error("femol_gmg_set_dist: out of device memory"); cudaGetLastError(); return FEMOL_E_CUDA;
+    }
+    g->dist = d;
+    return FEMOL_OK;
+}
+
+// After femol_gmg_setup[_lattice] of the strip hierarchy: gather the element matrices of level n_dist, assemble that
+// level's operator and rebuild the replicated hierarchy below it.  (The block-Jacobi inverses need no exchange: they are
+// only used on owned rows.)
+extern "C" int femol_gmg_dist_refresh(femol_gmg* g, void* stream) {
+    FEMOL_REQUIRE(g && g->dist, "femol_gmg_dist_refresh: not a distributed hierarchy");
+    cudaStream_t st = (cudaStream_t)stream;
+    GmgDist* d = g->dist;
+    const int S2 = 16 * g->nd * g->nd;
+    const Level& L = g->lv[d->n_dist];
+    const femol_strip& s = d->strip[d->n_dist];
+    // element row J (between node rows J and J + 1) belongs to the owner of node row J
+    const int64_t J0 = s.row0 + s.own_lo;                                       // global
+    int64_t J1 = s.row0 + s.own_hi; if (J1 > d->g_ny) J1 = d->g_ny;
+    const size_t total = (size_t)d->g_nx * d->g_ny * S2;
+    FEMOL_CUDA_CHECK(cudaMemsetAsync(d->gke, 0, total * sizeof(double), st));
+    if (J1 > J0)
+        FEMOL_CUDA_CHECK(cudaMemcpy2DAsync(d->gke + (size_t)J0 * S2, (size_t)d->g_ny * S2 * sizeof(double),
+                                           L.ke + (size_t)(J0 - s.row0) * S2, (size_t)L.ny * S2 * sizeof(double),
+                                           (size_t)(J1 - J0) * S2 * sizeof(double), (size_t)d->g_nx, cudaMemcpyDeviceToDevice, st));
+    int rc = femol_dist_allreduce(d->comm, d->gke, (int64_t)total, st);
+    if (rc != FEMOL_OK) return rc;
+    rc = femol_assemble(d->coarse_plan, d->gke, 1, nullptr, 0, nullptr, 1.0, d->coarse_fixed, nullptr, d->gvals, st);
+    if (rc != FEMOL_OK) return rc;
+    return gmg_setup_impl(d->coarse, d->gke, 1, nullptr, 0, nullptr, d->gvals, st);
+}
+
+extern "C" int femol_gmg_dist_exchange(femol_gmg* g, int level, double* x, int width, void* stream) {
+    FEMOL_REQUIRE(g && g->dist && x && level >= 0 && level <= g->dist->n_dist && width >= 1, "femol_gmg_dist_exchange: bad argument");
+    return femol_dist_exchange(g->dist->comm, x, width, g->dist->strip[level], (cudaStream_t)stream);
+}
+
+namespace {
+
+template <int ND>
+int dist_gather_solve(femol_gmg* g, cudaStream_t st) {
+    GmgDist* d = g->dist;
+    Level& L = g->lv[d->n_dist];
+    const femol_strip& s = d->strip[d->n_dist];
+    const int64_t rowd = s.row_nodes * ND;
+    const int64_t gn = d->coarse->lv[0].n;
+    FEMOL_CUDA_CHECK(cudaMemsetAsync(d->gr, 0, (size_t)gn * sizeof(double), st));
+    FEMOL_CUDA_CHECK(cudaMemcpyAsync(d->gr + (s.row0 + s.own_lo) * rowd, L.r + s.own_lo * rowd,
+                                     (size_t)(s.own_hi - s.own_lo) * rowd * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    int rc = femol_dist_allreduce(d->comm, d->gr, gn, st);
+    if (rc != FEMOL_OK) return rc;
+    rc = vcycle<ND>(d->coarse, 0, d->gr, d->ge, st, false);
+    if (rc != FEMOL_OK) return rc;
+    // every local row of the correction, ghost rows included (the level is replicated: no exchange)
+    FEMOL_CUDA_CHECK(cudaMemcpyAsync(L.e, d->ge + s.row0 * rowd, (size_t)s.n_rows * rowd * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return FEMOL_OK;
+}
+
+template <int ND>
+int dvcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, bool presmoothed) {
+    GmgDist* d = g->dist;
+    Level& L = g->lv[l];
+    Level& C = g->lv[l + 1];
+    const femol_strip& s = d->strip[l];
+    int rc;
+    if (!presmoothed) {
+        jacobi_kernel<ND, true><<<grid_for(L.n_nodes), 256, 0, st>>>(L.n_nodes, g->omega, L.dinv, r, nullptr, e);
+        FEMOL_LAUNCH_CHECK();
+    }
+    if ((rc = femol_dist_exchange(d->comm, e, ND, s, st)) != FEMOL_OK) return rc;
+    const femol_epilogue res = {FEMOL_EPI_RESIDUAL, r, nullptr, 0.0, nullptr, nullptr};
+    rc = L.vals32 ? femol_spmv_f32_epilogue_launch(L.plan, L.vals32, e, L.t, res, st)
+                  : femol_apply_epilogue_launch(L.plan, L.vals, e, L.t, res, st);
+    if (rc != FEMOL_OK) return rc;
+    if ((rc = femol_dist_exchange(d->comm, L.t, ND, s, st)) != FEMOL_OK) return rc;
+    const bool coarse_dist = l + 1 < d->n_dist;
+    FEMOL_CUDA_CHECK(femol_launch_pdl(restrict_kernel<ND>, dim3(grid_for(C.n_nodes)), dim3(256), 0, st, L.nx, L.ny, C.nx, C.ny,
+                                      (const uint8_t*)L.fixed, (const uint8_t*)C.fixed, (const double*)L.t, C.r,
+                                      (const double*)(coarse_dist ? C.dinv : nullptr), g->omega, C.e, (const int32_t*)L.lat_node));
+    femol_count_launch();
+    if (coarse_dist) {
+        if ((rc = dvcycle<ND>(g, l + 1, C.r, C.e, st, true)) != FEMOL_OK) return rc;
+        if ((rc = femol_dist_exchange(d->comm, C.e, ND, d->strip[l + 1], st)) != FEMOL_OK) return rc;
+    } else if ((rc = dist_gather_solve<ND>(g, st)) != FEMOL_OK) return rc;
+    if (femol_apply_has_jacobi(L.plan, L.vals)) {
+        FEMOL_CUDA_CHECK(femol_launch_pdl(prolong_add_kernel<ND>, dim3(grid_for(L.n_nodes)), dim3(256), 0, st, L.nx, L.ny, C.nx,
+                                          (const uint8_t*)L.fixed, (const double*)C.e, (const double*)e, L.t, (const int32_t*)L.lat_node));
+        femol_count_launch();
+        if ((rc = femol_dist_exchange(d->comm, L.t, ND, s, st)) != FEMOL_OK) return rc;
+        const femol_epilogue jac = {FEMOL_EPI_JACOBI, r, L.dinv, g->omega, nullptr, nullptr};
+        return L.vals32 ? femol_spmv_f32_epilogue_launch(L.plan, L.vals32, L.t, e, jac, st)
+                        : femol_apply_epilogue_launch(L.plan, L.vals, L.t, e, jac, st);
+    }
+    prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e, e, L.lat_node);
+    FEMOL_LAUNCH_CHECK();
+    if ((rc = femol_dist_exchange(d->comm, e, ND, s, st)) != FEMOL_OK) return rc;
+    return smooth<ND>(g, l, r, e, false, st);
+}
+
+}  // namespace
+
+int femol_gmg_dist_vcycle(femol_gmg* g, const double* r, double* z, cudaStream_t st, bool presmoothed) {
+    return g->nd == 2 ? dvcycle<2>(g, 0, r, z, st, presmoothed) : dvcycle<6>(g, 0, r, z, st, presmoothed);
 }

@@ -18,7 +18,8 @@ import ctypes
 
 import numpy as np
 
-__all__ = ['shard_items', 'Partition', 'DistributedStatic', 'init_process_group']
+__all__ = ['shard_items', 'Partition', 'DistributedStatic', 'init_process_group', 'StripPartition', 'DistributedSIMP_COMP',
+           'create_comm', 'coarsen_mask_host', 'owned_gather_index']
 
 
 def init_process_group(backend=None):
@@ -214,18 +215,381 @@ class DistributedStatic(object):
 
 
 def create_comm(F):
-    """NCCL communicator for femol_pcg_dist: rank 0 creates the unique id, torch.distributed broadcasts it."""
+    """NCCL communicator for femol_pcg_dist: rank 0 creates the unique id, torch.distributed broadcasts it.
+    Without an initialised process group: a communicator of one rank."""
     import torch
     import torch.distributed as dist
     L = F._lib
-    rank, world = dist.get_rank(), dist.get_world_size()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
     buf = (ctypes.c_char * 128)()
     if rank == 0:
         L.call('femol_dist_unique_id', buf)
-    t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device='cuda')
-    dist.broadcast(t, 0)
-    raw = bytes(t.cpu().tolist())
+    raw = bytes(buf)
+    if world > 1:
+        t = torch.tensor(list(raw), dtype=torch.uint8, device='cuda')
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().tolist())
     cbuf = ctypes.create_string_buffer(raw, 128)
     handle = ctypes.c_void_p()
     L.call('femol_dist_init', cbuf, rank, world, ctypes.byref(handle))
     return handle
+
+
+# =====================================================================================================================
+# Strip partition with multigrid: ONE large SIMP_COMP problem on the GPUs of a box (BASELINE config 5; SURVEY §8e)
+# =====================================================================================================================
+def _lattice_of(problem):
+    """(Nx, Ny, lat_node or None) of the problem's mesh: lattice cells per direction and lattice index -> node id
+    (None = identity, the rectangle_Q4 ordering)."""
+    shape = problem.structured_grid_shape()
+    if shape:
+        return shape[0], shape[1], None
+    lat = problem.node_lattice()
+    if lat is None:
+        raise ValueError('the strip partition needs a mesh whose nodes form a lattice (rectangle_Q4 / T3 / T6)')
+    return lat['Nx'], lat['Ny'], lat['lat_node'].astype(np.int64)
+
+
+def coarsen_mask_host(mask, nx, ny):
+    """Node mask of the next-coarser grid: coarse node (I, J) sits on fine node (min(2I, nx), min(2J, ny))
+    (csrc/gmg.cu coarsen_mask).  mask: [(ny+1)(nx+1)] lattice order."""
+    nxc, nyc = (nx + 1) // 2, (ny + 1) // 2
+    m = np.asarray(mask).reshape(ny + 1, nx + 1)
+    ii = np.minimum(2 * np.arange(nxc + 1), nx)
+    jj = np.minimum(2 * np.arange(nyc + 1), ny)
+    return np.ascontiguousarray(m[jj][:, ii]).reshape(-1), nxc, nyc
+
+
+class StripPartition(object):
+    """Strips of lattice rows for `world` ranks with `n_dist` distributed multigrid levels, seen from `rank`.
+
+    Node rows 0 .. Ny; rank r owns the rows [cuts[r], cuts[r+1]); interior cuts are multiples of A = 2^n_dist, so
+    that the owned rows of level l are [cuts[r] >> l, cuts[r+1] >> l) and a local grid that starts A rows below the
+    first owned row (and ends on the first row of the upper neighbour) coarsens exactly like the global grid:
+    level l of the strip = global rows [row0 >> l, top >> l] of global level l."""
+
+    def __init__(self, Ny, rank, world, n_dist, h_up0=1):
+        A = 1 << n_dist
+        self.Ny, self.rank, self.world, self.n_dist, self.A = int(Ny), rank, world, n_dist, A
+        cuts = [0] + [int(round(r * (Ny + 1) / float(world) / A)) * A for r in range(1, world)] + [Ny + 1]
+        self.cuts = cuts
+        if any(cuts[r + 1] - cuts[r] < max(A, 2) for r in range(world)):
+            raise ValueError('strips too thin: %d rows, %d ranks, %d distributed levels' % (Ny + 1, world, n_dist))
+        self.row0 = max(0, cuts[rank] - A) if rank > 0 else 0
+        self.top = cuts[rank + 1] if rank < world - 1 else Ny        # last local row (inclusive)
+        self.own_begin, self.own_end = cuts[rank], cuts[rank + 1]
+        ny_l = Ny
+        self.levels = []                                              # per level: dict(Ny, row0, top, own_begin, own_end)
+        for l in range(n_dist + 1):
+            last = rank == world - 1
+            lev = {'Ny': ny_l, 'row0': self.row0 >> l, 'own_begin': cuts[rank] >> l,
+                   'own_end': (ny_l + 1) if last else (cuts[rank + 1] >> l)}
+            lev['top'] = ny_l if last else lev['own_end']
+            lev['h_up'] = h_up0 if l == 0 else 1
+            lev['h_down'] = 1
+            self.levels.append(lev)
+            ny_l = (ny_l + 1) // 2
+
+    def local_ny(self, l=0):
+        return self.levels[l]['top'] - self.levels[l]['row0']
+
+    @staticmethod
+    def pick_levels(Nx, Ny, world, gather_nodes=40000, max_levels=8):
+        """Distributed levels: coarsen until the gathered level has at most `gather_nodes` nodes, keeping the strips
+        at least four alignment units high."""
+        n = 1
+        while n < max_levels:
+            nx_l, ny_l = Nx, Ny
+            for _ in range(n):
+                nx_l, ny_l = (nx_l + 1) // 2, (ny_l + 1) // 2
+            if (nx_l + 1) * (ny_l + 1) <= gather_nodes:
+                break
+            if (Ny + 1) // world < 4 * (1 << (n + 1)):
+                break
+            n += 1
+        return n
+
+
+def _gather_objects(obj, world):
+    if world == 1:
+        return [obj]
+    import torch.distributed as dist
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def owned_gather_index(own_global, n_total, world):
+    """Every rank contributes its owned items (global ids `own_global`) in a buffer padded to the largest count; the
+    all-gathered buffers are scattered to `index` (padding goes to the dummy slot n_total).  Returns (padded count,
+    index [world * padded count])."""
+    own_global = np.asarray(own_global, dtype=np.int64)
+    counts = _gather_objects(int(own_global.shape[0]), world)
+    assert sum(counts) == n_total, 'every item has exactly one owner'
+    m = max(counts)
+    pad = np.full(m, n_total, dtype=np.int64)
+    pad[:own_global.shape[0]] = own_global
+    return m, np.concatenate(_gather_objects(pad, world))
+
+
+def _dev_i64(values):
+    return (ctypes.c_int64 * len(values))(*[int(v) for v in values])
+
+
+class DistributedSIMP_COMP(object):
+    """SIMP_COMP (TOM_SIMP.py:13-81) on `world` GPUs for one large lattice mesh.
+
+    Every rank builds the same GLOBAL problem description on the host (mesh, domains, loads - never on the device),
+    cuts its strip out of it as an ordinary local FEM_Problem, and keeps the global density / sensitivity vectors
+    replicated on its GPU: assembly, multigrid set-up and the PCG run on the strip (halo exchanges + scalar
+    all-reduces inside the solve); the sensitivities of the owned elements are all-gathered, and the filter and the
+    OC update then run redundantly on every rank over the whole element set (they cost < 1 ms at 4 M elements and need
+    neighbours / a global volume constraint), so all ranks hold bit-identical densities without a broadcast."""
+
+    def __init__(self, F, global_problem, comm, volfrac=0.5, penal=3, rmin=1.5, n_dist=None, rank=None, world=None):
+        import torch
+        import torch.distributed as dist
+        from . import TOM_SIMP
+        self.F_mod, self.torch, self.comm = F, torch, comm
+        if rank is None or world is None:
+            rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+        self.rank, self.world = rank, world
+        gp = self.gp = global_problem
+        gm = gp.mesh
+        if gp.coating:
+            raise NotImplementedError('DistributedSIMP_COMP: coating formulation not distributed yet')
+        L = F._lib
+        nd = self.N_dof = gp.N_dof
+        ctype = self.ctype = gm.contains[0]
+        Nx, Ny, lat_node = _lattice_of(gp)
+        self.Nx, self.Ny = Nx, Ny
+        cells = np.asarray(gm.cells[ctype])
+        npx = Nx + 1
+        if lat_node is None:
+            node_row = np.arange(gm.N_nodes, dtype=np.int64) // npx
+            node_lat = None
+        else:
+            node_lat = np.empty(gm.N_nodes, dtype=np.int64)
+            node_lat[lat_node] = np.arange(gm.N_nodes, dtype=np.int64)
+            node_row = node_lat // npx
+        cell_rows = node_row[cells]
+        rmin_e, rmax_e = cell_rows.min(axis=1), cell_rows.max(axis=1)
+        h_up0 = int((rmax_e - rmin_e).max())
+        if n_dist is None:
+            n_dist = StripPartition.pick_levels(Nx, Ny, self.world)
+        part = self.part = StripPartition(Ny, self.rank, self.world, n_dist, h_up0=h_up0)
+        # ---- local mesh: lattice rows [row0, top], nodes renumbered in lattice order ------------------------
+        sel = (rmin_e >= part.row0) & (rmax_e <= part.top)
+        self.local_elements = np.nonzero(sel)[0]                       # global element ids, ascending
+        lat0 = part.row0 * npx
+        n_loc_nodes = (part.top - part.row0 + 1) * npx
+        g_nodes = np.arange(lat0, lat0 + n_loc_nodes, dtype=np.int64)
+        if lat_node is not None:
+            g_nodes = lat_node[g_nodes]
+        self.local_to_global = g_nodes
+        lc = cells[self.local_elements]
+        lc = (lc if node_lat is None else node_lat[lc]) - lat0
+        own = (rmin_e[sel] >= part.own_begin) & (rmin_e[sel] < part.own_end)     # element -> owner of its lowest row
+        # every element with a node on an owned row is local and stays inside the rows a halo exchange fills
+        touch = (rmax_e >= part.own_begin) & (rmin_e <= part.own_end - 1)
+        lo_ok = part.own_begin - (h_up0 if self.rank > 0 else 0)
+        hi_ok = part.own_end - 1 + (part.levels[0]['h_down'] if self.rank < self.world - 1 else 0)
+        assert sel[touch].all() and (rmin_e[touch] >= lo_ok).all() and (rmax_e[touch] <= hi_ok).all(), \
+            'an element of an owned row reaches beyond the exchanged halo rows'
+        kw = {'quad_element': gm.ElementClasses['quad']} if ctype == 'quad' else {'tri_element': gm.ElementClasses['triangle']}
+        lm = self.local_mesh = F.Mesh(gm.points[g_nodes], {ctype: lc}, structured=gm.structured, **kw)
+        assert lm.N_nodes == n_loc_nodes, 'every local lattice node is used by a local element'
+        lp = self.local_problem = F.FEM_Problem(gp.physics, gp.model, lm)
+        lp.define_materials(*gp.materials)
+        lp.tensors, lp.ho = gp.tensors, gp.ho
+        lp.fixed_domains, lp.fixed_ddls = list(gp.fixed_domains), list(gp.fixed_ddls)
+        Fg = np.array(gp.F, dtype=np.float64)
+        lp.F = Fg[(g_nodes[:, None] * nd + np.arange(nd)[None]).reshape(-1)]
+        lp.forces, lp.force_domains = list(gp.forces), list(gp.force_domains)
+        lp.preconditioner, lp.gmg_hourglass = 'gmg', False
+        lp.solver_rtol, lp.solver_max_iter = gp.solver_rtol, gp.solver_max_iter
+        lp.gmg_smoothing_steps, lp.gmg_omega = 1, gp.gmg_omega
+        lp.on_nonconvergence = gp.on_nonconvergence
+        d = lp.device
+        dev = d.dev
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+        # ---- replicated SIMP state over ALL elements ---------------------------------------------------------
+        self.f, self.p, self.rmin = volfrac, penal, rmin
+        self.n_elem = cells.shape[0]
+        self._x = torch.full((self.n_elem,), float(volfrac), dtype=torch.float64, device=dev)
+        self._xn = torch.empty_like(self._x)
+        self._dc = torch.zeros_like(self._x)
+        self._dcf = torch.empty_like(self._x)
+        self._scal = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._red_ws = torch.zeros(int(L.load().femol_reduce_workspace_doubles()), dtype=torch.float64, device=dev)
+        gm.compute_element_centers()
+        self._filter = TOM_SIMP.build_filter(gm, rmin, dev)
+        self._mask = None
+        self._loc_elems = up(self.local_elements, np.int64)
+        own_local = np.nonzero(own)[0]
+        self._own_local = up(own_local, np.int64)
+        own_global = self.local_elements[own_local]
+        self._own_max, index = owned_gather_index(own_global, self.n_elem, self.world)
+        self._gather_index = up(index, np.int64)
+        self._send = torch.zeros(self._own_max, dtype=torch.float64, device=dev)
+        self._recv = torch.empty(self._own_max * self.world, dtype=torch.float64, device=dev)
+        self._dc_pad = torch.zeros(self.n_elem + 1, dtype=torch.float64, device=dev)
+        self._x_loc = torch.empty(d.n_elem, dtype=torch.float64, device=dev)
+        self._dc_loc = torch.empty(d.n_elem, dtype=torch.float64, device=dev)
+        self._scal_loc = torch.zeros(8, dtype=torch.float64, device=dev)
+        # ---- hierarchy: local strip levels + the replicated coarse hierarchy ----------------------------------
+        self._U = torch.zeros(d.n, dtype=torch.float64, device=dev)
+        self._ws = None
+        self._gmg = None
+        self._coarse = None
+        self.solver_info = {}
+        self.iteration_log = []
+        self.loop, self.change, self.c = 0, 1.0, None
+        self._global_mask_lat = self._global_fixed_mask(lat_node)
+
+    # ---- set-up helpers ---------------------------------------------------------------------------------------
+    def _global_fixed_mask(self, lat_node):
+        gp, gm = self.gp, self.gp.mesh
+        mask = np.zeros(gm.N_nodes, dtype=np.uint8)
+        for domain, ddls in zip(gp.fixed_domains, gp.fixed_ddls):
+            mask[gm.domain_nodes(domain)] |= np.uint8(sum(1 << int(k) for k in ddls))
+        return mask if lat_node is None else mask[lat_node]
+
+    def _build_hierarchy(self):
+        """Local hierarchy (created and first refreshed by the local problem), truncated to n_dist + 1 levels, plus the
+        replicated lattice hierarchy over the global level-n_dist grid."""
+        torch, F, L = self.torch, self.F_mod, self.F_mod._lib
+        lp, part, nd = self.local_problem, self.part, self.N_dof
+        d = lp.device
+        g = lp._gmg_ready()
+        info = (ctypes.c_int64 * 64)()
+        L.call('femol_gmg_info', g, info)
+        if int(info[0]) < part.n_dist + 1:
+            raise ValueError('the local hierarchy has %d levels, %d needed' % (int(info[0]), part.n_dist + 1))
+        for l, lev in enumerate(part.levels):
+            assert int(info[2 + 2 * l]) == lev['top'] - lev['row0'], 'local level %d does not match the partition' % l
+        L.call('femol_gmg_truncate', g, part.n_dist + 1)
+        # global grid of level n_dist and its node mask
+        mask, nx, ny = self._global_mask_lat, self.Nx, self.Ny
+        for _ in range(part.n_dist):
+            mask, nx, ny = coarsen_mask_host(mask, nx, ny)
+        assert ny == part.levels[-1]['Ny'] and nx == int(info[1 + 2 * part.n_dist])
+        a = np.add.outer(np.arange(nx), (nx + 1) * np.arange(ny)).reshape(-1)           # e = I * ny + J
+        conn = np.stack([a, a + 1, a + nx + 2, a + nx + 1], axis=1).astype(np.int32)
+        up = lambda arr, dt: torch.from_numpy(np.ascontiguousarray(arr, dtype=dt)).to(d.dev)
+        self._c_conn = up(conn, np.int32)
+        n_nodes = (nx + 1) * (ny + 1)
+        cplan = ctypes.c_void_p()
+        L.call('femol_plan_create', nx * ny, 4, nd, n_nodes, L.ptr(self._c_conn), L.stream(), ctypes.byref(cplan))
+        self._c_plan = cplan
+        self._c_mask = up(mask, np.uint8)
+        nxc, nyc = (nx + 1) // 2, (ny + 1) // 2
+        e = np.arange(nx * ny)
+        parent = (e // ny // 2) * nyc + (e % ny) // 2
+        order = np.argsort(parent, kind='stable')
+        ptr = np.concatenate([[0], np.cumsum(np.bincount(parent, minlength=nxc * nyc))])
+        ident = np.arange(n_nodes, dtype=np.int32)
+        self._c_lat = [up(ident, np.int32), up(ident, np.int32), up(ptr, np.int32), up(order, np.int32)]
+        ch = ctypes.c_void_p()
+        L.call('femol_gmg_create_lattice', nx, ny, nd, cplan, L.ptr(self._c_mask), L.ptr(self._c_lat[0]), L.ptr(self._c_lat[1]),
+               L.ptr(self._c_lat[2]), L.ptr(self._c_lat[3]), 1, float(lp.gmg_omega), L.stream(), ctypes.byref(ch))
+        torch.cuda.current_stream().synchronize()
+        self._coarse = ch
+        lv = part.levels
+        L.call('femol_gmg_set_dist', g, self.comm, part.n_dist, _dev_i64([v['row0'] for v in lv]),
+               _dev_i64([v['own_begin'] for v in lv]), _dev_i64([v['own_end'] for v in lv]),
+               (ctypes.c_int * len(lv))(*[v['h_up'] for v in lv]), (ctypes.c_int * len(lv))(*[v['h_down'] for v in lv]),
+               ch, cplan, L.ptr(self._c_mask))
+        self._gmg = g
+
+    def __del__(self):
+        try:
+            L = self.F_mod._lib.load()
+            self.local_problem._destroy_gmg()
+            if self._coarse is not None:
+                L.femol_gmg_destroy(self._coarse)
+                L.femol_plan_destroy(self._c_plan)
+        except Exception:
+            pass
+
+    # ---- one SIMP iteration ----------------------------------------------------------------------------------------
+    def solve_displacement(self):
+        """Assemble K(x^p) on the strip, refresh both hierarchies, distributed multigrid PCG -> local U (device)."""
+        torch, L = self.torch, self.F_mod._lib
+        lp = self.local_problem
+        d = lp.device
+        torch.index_select(self._x, 0, self._loc_elems, out=self._x_loc)
+        lp.assemble('K', X=self._x_loc, p=self.p)
+        if self._gmg is None:
+            self._build_hierarchy()
+        else:
+            lp._gmg_ready()
+        L.call('femol_gmg_dist_refresh', self._gmg, L.stream())
+        if self._ws is None:
+            self._ws = torch.empty(int(L.load().femol_pcg_gmg_dist_workspace_doubles(d.plan)), dtype=torch.float64, device=d.dev)
+        iters, relres = ctypes.c_int(0), ctypes.c_double(0.0)
+        rc = L.call('femol_pcg_gmg_dist', d.plan, self._gmg, L.ptr(lp._Kv), L.ptr(lp._F_dev), L.ptr(self._U),
+                    float(lp.solver_rtol), int(lp.solver_max_iter), L.ptr(self._ws), ctypes.byref(iters), ctypes.byref(relres),
+                    L.stream())
+        converged = rc == 0 or (rc == L.S_STAGNATED and relres.value <= lp.stagnation_bound)
+        self.solver_info = {'iterations': iters.value, 'relres': relres.value, 'status': rc, 'converged': converged,
+                            'preconditioner': 'gmg-dist'}
+        if rc == L.S_BREAKDOWN:
+            raise L.FemolError('distributed PCG breakdown after %d iterations' % iters.value)
+        if not converged:
+            lp._report_nonconvergence('distributed PCG did not converge: %d iterations, relative residual %.3e (rtol %.1e)'
+                                      % (iters.value, relres.value, lp.solver_rtol))
+        return self._U
+
+    def iterate(self):
+        torch, L = self.torch, self.F_mod._lib
+        import torch.distributed as dist
+        lp = self.local_problem
+        d = lp.device
+        self.solve_displacement()
+        Eb, pe_b = lp._element_matrices('K', False)
+        pc = self.p if lp.mesh.structured else 2 * self.p               # FEM.py:630-631 double penalisation quirk
+        L.call('femol_sens_compliance', d.plan, L.ptr(Eb), pe_b, None, 0, L.ptr(self._U), L.ptr(self._x_loc), float(self.p),
+               float(pc), float(pc - 1), L.ptr(self._dc_loc), L.ptr(self._scal_loc), L.ptr(d.red_ws), L.stream())
+        # owned elements: sensitivities -> all ranks; compliance c = sum_e x^pc q_e = -sum_e x_e dc_e / p
+        dc_own = self._dc_loc[self._own_local]
+        n_own = dc_own.shape[0]
+        self._send[:n_own] = dc_own
+        c_loc = -(dc_own * self._x_loc[self._own_local]).sum() / float(self.p)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._recv, self._send)
+            dist.all_reduce(c_loc)
+        else:
+            self._recv.copy_(self._send)
+        self._dc_pad[self._gather_index] = self._recv
+        self._dc.copy_(self._dc_pad[:self.n_elem])
+        self._scal[0] = c_loc
+        from . import TOM_SIMP
+        TOM_SIMP.apply_filter(self._filter, self._x, self._dc, self._dcf)
+        L.call('femol_oc_update', self.n_elem, L.ptr(self._x), L.ptr(self._dcf), 0, float(self.f), None, L.ptr(self._mask),
+               L.ptr(self._xn), self._scal.data_ptr() + 4 * 8, L.ptr(self._red_ws), L.stream())
+        self._x, self._xn = self._xn, self._x
+        s = self._scal.cpu().numpy()
+        self.c, self.change = float(s[0]), float(s[4])
+        return self.change, self.c
+
+    def solve(self, converge=0.01, max_iter=100):
+        self.change, self.loop = 1.0, 0
+        while self.change > converge and self.loop < max_iter:
+            self.loop += 1
+            self.iterate()
+            info = dict(self.solver_info)
+            info.update(loop=self.loop, change=self.change, c=self.c)
+            self.iteration_log.append(info)
+        return self.density()
+
+    def density(self):
+        """Global densities (host array; identical on every rank)."""
+        return self._x.cpu().numpy()
+
+    def owned_displacement(self):
+        """(global node ids of the owned rows, their displacements [n_owned_nodes, N_dof]) as host arrays."""
+        part, npx, nd = self.part, self.Nx + 1, self.N_dof
+        lo, hi = (part.own_begin - part.row0) * npx, (part.own_end - part.row0) * npx
+        U = self._U.view(-1, nd)[lo:hi].cpu().numpy()
+        return self.local_to_global[lo:hi], U

@@ -218,6 +218,33 @@ int femol_pcg_dist(femol_plan_t plan, femol_comm_t comm, int64_t n_owned_nodes, 
                    const int64_t* h_recv_count, const double* vals, const double* f, double* u, double rtol,
                    int max_iter, int precond, double* ws, int* h_iters, double* h_relres, void* stream);
 
+/* ---- multi-GPU strip partition with multigrid (BASELINE config 5) ------------------------------------
+ * One LARGE problem on the GPUs of a box, for meshes whose nodes form a lattice (rectangle_Q4 / T3 / T6): rank r owns
+ * the lattice rows [cut_r, cut_r+1), cuts being multiples of 2^n_dist rows, and holds the rows [cut_r - 2^n_dist,
+ * cut_r+1] as an ordinary LOCAL mesh (femol_b200/dist.py StripPartition).  Its hierarchy is the single-GPU one
+ * (femol_gmg_create / _create_lattice + femol_gmg_setup / _setup_lattice on the local mesh), cut after n_dist + 1
+ * levels by femol_gmg_truncate: the alignment of the cuts makes every local element matrix of every level the global
+ * one, so the set-up of the distributed levels needs no communication.  femol_gmg_set_dist attaches the strip
+ * description (per level 0..n_dist: global row of the local grid's first row, owned global rows [begin, end), rows moved
+ * up / down by a halo exchange) and `coarse`, a complete lattice hierarchy (Q4, identity numbering, plan `coarse_plan`,
+ * node mask `coarse_fixed`) that EVERY rank holds for the whole level-n_dist grid; all borrowed.
+ * femol_gmg_dist_refresh (after each femol_gmg_setup*) all-reduces the element matrices of level n_dist, assembles
+ * that level and rebuilds `coarse`.  A V-cycle exchanges halo rows before every operator that reads neighbours
+ * (4 per distributed level) and gathers the level-n_dist residual for the replicated coarse solve.
+ * femol_pcg_gmg_dist: multigrid PCG on the strip (local plan / vals / f / u over ALL local rows; results valid on the
+ * owned rows, the ghost rows of u are refreshed at the end); every dot product is an all-reduce of device scalars.
+ * femol_gmg_dist_exchange: fill the ghost rows of a level-`level` vector (width doubles per node). */
+int femol_gmg_truncate(femol_gmg_t gmg, int n_levels);
+int femol_gmg_set_dist(femol_gmg_t gmg, femol_comm_t comm, int n_dist, const int64_t* h_row0, const int64_t* h_own_begin,
+                       const int64_t* h_own_end, const int* h_up, const int* h_down, femol_gmg_t coarse,
+                       femol_plan_t coarse_plan, const uint8_t* coarse_fixed);
+int femol_gmg_dist_refresh(femol_gmg_t gmg, void* stream);
+int femol_gmg_dist_exchange(femol_gmg_t gmg, int level, double* x, int width, void* stream);
+int femol_dist_allreduce_sum(femol_comm_t comm, double* buf, int64_t count, void* stream);
+int64_t femol_pcg_gmg_dist_workspace_doubles(femol_plan_t plan);
+int femol_pcg_gmg_dist(femol_plan_t plan, femol_gmg_t gmg, const double* vals, const double* f, double* u, double rtol,
+                       int max_iter, double* ws, int* h_iters, double* h_relres, void* stream);
+
 /* ---- K6: block kernels for LOBPCG (replaces the dense eigh(K, M) of FEM.py:277 / eigsh of FEM.py:234) ----
  * The Rayleigh-Ritz outer iteration (3m x 3m pencil, m <= 16) is host logic (femol_b200/lobpcg.py); all
  * O(n) work is here.  Block vectors are row-major [n][ld] (the m values of one dof contiguous).

@@ -1,0 +1,109 @@
+"""Strip-distributed SIMP_COMP against the single-GPU SIMP_COMP on the same problem.
+
+    python tools/dist_simp_check.py --mesh q4 --nx 96 --ny 48 --iters 3                      (one rank)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/dist_simp_check.py --mesh t6 --nx 64 --ny 64 --iters 3
+
+Prints one JSON line (rank 0) and exits non-zero when the distributed run departs from the single-GPU one."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+
+def build_problem(F, kind, nx, ny, model='plane'):
+    Lx, Ly = float(nx), float(ny)
+    mesh = {'q4': F.mesh.rectangle_Q4, 't3': F.mesh.rectangle_T3, 't6': F.mesh.rectangle_T6}[kind](Lx, Ly, nx, ny)
+    gp = F.FEM_Problem('displacement', model, mesh)
+    if model == 'plane':
+        gp.define_materials(F.materials.general_isotropic()); gp.define_tensors(1)
+        gp.add_fixed_domain(F.domains.inside_box([0], [[0, Ly]]), ddls=[0, 1])
+        gp.add_forces([0, -1.0], F.domains.inside_box([Lx], [[Ly / 2 - 1, Ly / 2 + 1]]))
+    else:
+        gp.define_materials(F.materials.IsotropicMaterial(10920, 0.3, 1)); gp.define_tensors(2.0)
+        gp.add_fixed_domain(F.domains.inside_box([0], [[0, Ly]]))
+        gp.add_forces([0, 0, -1e-2, 0, 0, 0], F.domains.inside_box([Lx], [[0, Ly]]))
+    return gp
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--mesh', default='q4')
+    ap.add_argument('--model', default='plane')
+    ap.add_argument('--nx', type=int, default=96)
+    ap.add_argument('--ny', type=int, default=48)
+    ap.add_argument('--iters', type=int, default=3)
+    ap.add_argument('--ndist', type=int, default=None)
+    ap.add_argument('--rtol', type=float, default=1e-9)
+    ap.add_argument('--no-reference', action='store_true', help='skip the single-GPU run (large meshes)')
+    ap.add_argument('--out', default=None)
+    a = ap.parse_args()
+    import femol_b200 as F
+    from femol_b200 import dist as fd
+    rank, world = fd.init_process_group()
+    if world == 1:
+        torch.cuda.set_device(0)
+    t0 = time.perf_counter()
+    gp = build_problem(F, a.mesh, a.nx, a.ny, a.model)
+    gp.solver_rtol = a.rtol
+    comm = fd.create_comm(F)
+    opt = fd.DistributedSIMP_COMP(F, gp, comm, volfrac=0.4, penal=3, rmin=1.5, n_dist=a.ndist)
+    t_setup = time.perf_counter() - t0
+    times, log = [], []
+    for it in range(a.iters):
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        t1 = time.perf_counter()
+        change, c = opt.iterate()
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t1)
+        log.append({'c': c, 'change': change, 'pcg': opt.solver_info['iterations'], 'relres': opt.solver_info['relres'],
+                    'status': opt.solver_info['status']})
+    X = opt.density()
+    res = {'mesh': a.mesh, 'model': a.model, 'nx': a.nx, 'ny': a.ny, 'world': world, 'n_dist': opt.part.n_dist, 'cuts': opt.part.cuts,
+           'ndof': int(gp.mesh.N_nodes * gp.N_dof), 'setup_s': t_setup, 'iteration_s': times, 'log': log,
+           'gpu_mem_gb': torch.cuda.max_memory_allocated() / 1e9}
+    ok = True
+    if not a.no_reference and rank == 0:
+        ref = build_problem(F, a.mesh, a.nx, a.ny, a.model)
+        ref.solver_rtol = a.rtol
+        so = F.SIMP_COMP(ref, volfrac=0.4, penal=3, rmin=1.5)
+        so.archive = False
+        ref_log, ref_times = [], []
+        for it in range(a.iters):
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            change, c = so.iterate()
+            torch.cuda.synchronize()
+            ref_times.append(time.perf_counter() - t1)
+            ref_log.append({'c': c, 'change': change, 'pcg': ref.solver_info['iterations']})
+        res['ref_iteration_s'] = ref_times
+        Xr = so.density()
+        res['ref_log'] = ref_log
+        res['density_err'] = float(np.abs(X - Xr).max())
+        res['c_rel_err'] = [abs(l['c'] - r['c']) / abs(r['c']) for l, r in zip(log, ref_log)]
+        ok = res['density_err'] < 1e-4 and max(res['c_rel_err']) < 1e-6
+    res['ok'] = ok
+    if rank == 0:
+        line = json.dumps(res)
+        print(line)
+        if a.out:
+            with open(a.out, 'a') as fh:
+                fh.write(line + '\n')
+    if world > 1:
+        torch.distributed.barrier()
+        F._lib.load().femol_dist_destroy(comm)
+        torch.distributed.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == '__main__':
+    main()
