@@ -67,6 +67,10 @@ SIGNATURES = {
     'femol_gmg_dist_refresh': (c_int, [P, P]),
     'femol_gmg_dist_exchange': (c_int, [P, c_int, P, c_int, P]),
     'femol_dist_allreduce_sum': (c_int, [P, P, c_i64, P]),
+    'femol_gmg_dist_p2p_sizes': (c_int, [P, ctypes.POINTER(c_i64)]),
+    'femol_dist_p2p_open': (c_int, [P, c_i64, c_i64, P]),
+    'femol_dist_p2p_attach': (c_int, [P, P]),
+    'femol_dist_p2p_status': (c_int, [P, ctypes.POINTER(c_i64)]),
     'femol_pcg_gmg_dist_workspace_doubles': (c_i64, [P]),
     'femol_pcg_gmg_dist': (c_int, [P, P, P, P, P, c_dbl, c_int, P, ctypes.POINTER(c_int), ctypes.POINTER(c_dbl), P]),
     'femol_spmm': (c_int, [P, P, P, c_int, P, c_int, c_int, P]),

@@ -70,9 +70,38 @@ int load_nccl() {
 
 }  // namespace
 
+// Peer-memory transport (femol_dist_p2p_open / _attach): every rank owns one cudaMalloc'ed WINDOW that all other ranks
+// of the box map through CUDA IPC (NVLink / NVSwitch peer stores).  Layout of a window:
+//   [P2P_OFF_FLAGS]   u64 halo_flag[2] (last epoch pushed by the lower / upper neighbour), red_flag[16], gat_flag[16]
+//   [P2P_OFF_RED]     double red[2 parities][16 ranks][16]      partial sums of the scalar all-reduce
+//   [P2P_OFF_HALO]    double halo[2 (from lower, from upper)][2 parities][halo_doubles]
+//   [off_gather]      double gather[2 parities][gather_doubles]
+// A transfer = the sender's kernel stores the payload into the receiver's window (slot = epoch parity), fences at system
+// scope and releases the receiver's flag with its epoch; the receiver's kernel spins on its own flag (acquire) and
+// copies the slot out.  Epochs are DEVICE counters advanced by the kernels themselves, so the launch sequence is static
+// (CUDA-graph capturable).  Two parities suffice: a rank can only push epoch k + 2 after it completed transfer k + 1,
+// which needed the receiver's push k + 1, which the receiver's stream issues after its transfer-k kernel has finished.
+constexpr int P2P_MAX_RANKS = 16;
+constexpr int P2P_RED_MAX = 16;
+constexpr size_t P2P_OFF_FLAGS = 0, P2P_OFF_RED = 1024, P2P_OFF_HALO = 8192;
+enum { P2P_C_HALO_EP = 0, P2P_C_HALO_ARRIVE = 1, P2P_C_HALO_DONE = 2, P2P_C_RED_EP = 3, P2P_C_GAT_EP = 4, P2P_C_GAT_ARRIVE = 5,
+       P2P_C_GAT_DONE = 6, P2P_C_ERR = 7, P2P_C_N = 8 };
+
+struct P2PPeers { char* w[P2P_MAX_RANKS]; };
+
+struct femol_p2p {
+    bool on;
+    char* win;                       // my window
+    size_t win_bytes, halo_doubles, gather_doubles, off_gather;
+    P2PPeers peers;                  // every rank's window as mapped here (peers.w[rank] = win)
+    unsigned long long* ctr;         // device counters (local): epochs, arrival tickets, error flag
+    long long n_halo, n_red, n_gather;   // host-side statistics
+};
+
 struct femol_comm {
     ncclComm_t comm;
     int rank, nranks;
+    femol_p2p p2p;
 };
 
 namespace {
@@ -306,6 +335,7 @@ extern "C" int femol_dist_init(const void* unique_id128, int rank, int nranks, f
     memcpy(&id, unique_id128, sizeof(id));
     femol_comm* c = new femol_comm();
     c->rank = rank; c->nranks = nranks; c->comm = nullptr;
+    memset(&c->p2p, 0, sizeof(c->p2p));
     ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
     if (r != 0) { femol_set_error("ncclCommInitRank -> %s", g_nccl.GetErrorString(r)); delete c; return FEMOL_E_CUDA; }
     *out = c;
@@ -314,6 +344,13 @@ extern "C" int femol_dist_init(const void* unique_id128, int rank, int nranks, f
 
 extern "C" int femol_dist_destroy(femol_comm* c) {
     if (!c) return FEMOL_OK;
+    if (c->p2p.win) {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < c->nranks; ++r)
+            if (r != c->rank && c->p2p.peers.w[r]) cudaIpcCloseMemHandle(c->p2p.peers.w[r]);
+        cudaFree(c->p2p.win); cudaFree(c->p2p.ctr);
+        cudaGetLastError();
+    }
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     delete c;
     return FEMOL_OK;
@@ -354,10 +391,147 @@ extern "C" int femol_pcg_dist(femol_plan_t plan, femol_comm* comm, int64_t n_own
 int femol_comm_rank(const femol_comm* c) { return c->rank; }
 int femol_comm_size(const femol_comm* c) { return c->nranks; }
 
+namespace {
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *flag >= ep; gives up after ~2 s (a peer died): raises the error counter, every later wait returns at once
+__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long ep, unsigned long long* ctr) {
+    if (ld_volatile_u64(&ctr[P2P_C_ERR]) != 0ULL) return;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < ep) {
+        if (clock64() - t0 > 4000000000LL) { atomicExch(&ctr[P2P_C_ERR], 1ULL); return; }
+    }
+}
+__device__ __forceinline__ unsigned long long* win_flags(char* w) { return reinterpret_cast<unsigned long long*>(w + P2P_OFF_FLAGS); }
+
+__device__ __forceinline__ void copy_d2(double* __restrict__ dst, const double* __restrict__ src, int64_t n, bool from_window) {
+    // n is even and both pointers are 16-byte aligned (rows of an even number of doubles)
+    const int64_t n2 = n >> 1;
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
+        d2[i] = from_window ? __ldcg(&s2[i]) : s2[i];
+}
+
+// Halo exchange of one vector in ONE CTA (messages are a few lattice rows: 30 - 270 KB): push my boundary rows into the
+// neighbours' windows, fence, release their flags, acquire mine, copy the rows out.  No grid-level tickets: every
+// microsecond of this kernel is on the critical path of the V-cycle (13 exchanges per CG iteration).
+__device__ __forceinline__ void cta_copy_d2(double* __restrict__ dst, const double* __restrict__ src, int64_t n, bool from_window) {
+    const int64_t n2 = n >> 1;
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    for (int64_t i = threadIdx.x; i < n2; i += blockDim.x) d2[i] = from_window ? __ldcg(&s2[i]) : s2[i];
+}
+
+__global__ void __launch_bounds__(1024)
+p2p_halo_kernel(double* x, int64_t rowd, int64_t own_lo, int64_t own_hi, int h_up, int h_down, int lower, int upper, int me,
+                P2PPeers peers, size_t hmax, unsigned long long* ctr) {
+    const unsigned long long ep = ld_volatile_u64(&ctr[P2P_C_HALO_EP]) + 1ULL;
+    const size_t par = (size_t)(ep & 1ULL);
+    if (lower >= 0)   // my bottom owned rows -> the lower neighbour's "from upper" slot
+        cta_copy_d2(reinterpret_cast<double*>(peers.w[lower] + P2P_OFF_HALO) + (2 + par) * hmax, x + own_lo * rowd, h_down * rowd, false);
+    if (upper >= 0)   // my top owned rows -> the upper neighbour's "from lower" slot
+        cta_copy_d2(reinterpret_cast<double*>(peers.w[upper] + P2P_OFF_HALO) + (0 + par) * hmax, x + (own_hi - h_up) * rowd, h_up * rowd, false);
+    __threadfence_system();
+    __syncthreads();           // every thread has read the epoch and its stores are performed system-wide
+    unsigned long long* mine = win_flags(peers.w[me]);
+    if (threadIdx.x == 0 && lower >= 0) { st_release_sys(&win_flags(peers.w[lower])[1], ep); wait_flag(&mine[0], ep, ctr); }
+    if (threadIdx.x == 32 && upper >= 0) { st_release_sys(&win_flags(peers.w[upper])[0], ep); wait_flag(&mine[1], ep, ctr); }
+    __syncthreads();
+    const double* box = reinterpret_cast<const double*>(peers.w[me] + P2P_OFF_HALO);
+    if (lower >= 0) cta_copy_d2(x + (own_lo - h_up) * rowd, box + (0 + par) * hmax, h_up * rowd, true);
+    if (upper >= 0) cta_copy_d2(x + own_hi * rowd, box + (2 + par) * hmax, h_down * rowd, true);
+    if (threadIdx.x == 0) ctr[P2P_C_HALO_EP] = ep;
+}
+
+// In-place sum of `count` (<= 16) doubles over all ranks: every rank stores its values into every window, then adds the
+// W contributions in rank order (bit-identical result on all ranks).  One CTA.
+__global__ void __launch_bounds__(256)
+p2p_allreduce_kernel(double* buf, int count, int W, int me, P2PPeers peers, unsigned long long* ctr) {
+    const unsigned long long ep = ld_volatile_u64(&ctr[P2P_C_RED_EP]) + 1ULL;
+    const size_t par = (size_t)(ep & 1ULL);
+    const int t = threadIdx.x;
+    if (t < W * count) {
+        const int peer = t / count, k = t - peer * count;
+        reinterpret_cast<double*>(peers.w[peer] + P2P_OFF_RED)[(par * P2P_MAX_RANKS + me) * P2P_RED_MAX + k] = buf[k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < W) {
+        st_release_sys(&win_flags(peers.w[t])[2 + me], ep);
+        wait_flag(&win_flags(peers.w[me])[2 + t], ep, ctr);
+    }
+    __syncthreads();
+    if (t < count) {
+        const double* red = reinterpret_cast<const double*>(peers.w[me] + P2P_OFF_RED) + par * P2P_MAX_RANKS * P2P_RED_MAX;
+        double sum = 0.0;
+        for (int r = 0; r < W; ++r) sum += __ldcg(&red[r * P2P_RED_MAX + t]);
+        buf[t] = sum;
+    }
+    if (t == 0) ctr[P2P_C_RED_EP] = ep;
+}
+
+// All-gather by pushes: my `count` doubles go to offset `goff` of the gather slot of EVERY window; once all W pieces
+// have arrived the slot (total doubles) is copied to `out`.
+__global__ void __launch_bounds__(256)
+p2p_gather_kernel(const double* __restrict__ src, int64_t count, int64_t goff, int64_t total, double* __restrict__ out, int W, int me,
+                  P2PPeers peers, size_t off_gather, size_t gmax, unsigned long long* ctr) {
+    __shared__ unsigned long long s_ep;
+    if (threadIdx.x == 0) s_ep = ld_volatile_u64(&ctr[P2P_C_GAT_EP]) + 1ULL;
+    __syncthreads();
+    const unsigned long long ep = s_ep;
+    const size_t par = (size_t)(ep & 1ULL);
+    for (int r = 0; r < W; ++r) {
+        const int peer = (me + r) % W;      // spread the ranks' first targets over the switch
+        copy_d2(reinterpret_cast<double*>(peers.w[peer] + off_gather) + par * gmax + goff, src, count, false);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = atomicAdd(&ctr[P2P_C_GAT_ARRIVE], 1ULL);
+        if (t == (unsigned long long)gridDim.x - 1ULL) {
+            ctr[P2P_C_GAT_ARRIVE] = 0ULL;
+            __threadfence();
+            for (int r = 0; r < W; ++r) st_release_sys(&win_flags(peers.w[r])[2 + P2P_MAX_RANKS + me], ep);
+        }
+    }
+    if (threadIdx.x < W) wait_flag(&win_flags(peers.w[me])[2 + P2P_MAX_RANKS + threadIdx.x], ep, ctr);
+    __syncthreads();
+    copy_d2(out, reinterpret_cast<const double*>(peers.w[me] + off_gather) + par * gmax, total, true);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long t = atomicAdd(&ctr[P2P_C_GAT_DONE], 1ULL);
+        if (t == (unsigned long long)gridDim.x - 1ULL) { ctr[P2P_C_GAT_DONE] = 0ULL; ctr[P2P_C_GAT_EP] = ep; }
+    }
+}
+
+}  // namespace
+
 int femol_dist_exchange(femol_comm* c, double* x, int width, const femol_strip& s, cudaStream_t st) {
     if (c->nranks == 1) return FEMOL_OK;
     const int64_t rowd = s.row_nodes * width;
     const bool lower = c->rank > 0, upper = c->rank < c->nranks - 1;
+    const int64_t hmaxrows = s.h_up > s.h_down ? s.h_up : s.h_down;
+    if (c->p2p.on && (size_t)(hmaxrows * rowd) <= c->p2p.halo_doubles && (rowd & 1) == 0 && ((uintptr_t)x & 15) == 0) {
+        p2p_halo_kernel<<<1, 1024, 0, st>>>(x, rowd, s.own_lo, s.own_hi, s.h_up, s.h_down, lower ? c->rank - 1 : -1,
+                                            upper ? c->rank + 1 : -1, c->rank, c->p2p.peers, c->p2p.halo_doubles, c->p2p.ctr);
+        FEMOL_LAUNCH_CHECK();
+        ++c->p2p.n_halo;
+        return FEMOL_OK;
+    }
     NCCL_CHECK(g_nccl.GroupStart());
     if (lower) {
         NCCL_CHECK(g_nccl.Send(x + s.own_lo * rowd, (size_t)(s.h_down * rowd), ncclDouble_, c->rank - 1, c->comm, st));
@@ -373,8 +547,86 @@ int femol_dist_exchange(femol_comm* c, double* x, int width, const femol_strip& 
 
 int femol_dist_allreduce(femol_comm* c, double* buf, int64_t count, cudaStream_t st) {
     if (c->nranks == 1 || count == 0) return FEMOL_OK;
+    if (c->p2p.on && count <= P2P_RED_MAX && c->nranks * count <= 256) {
+        p2p_allreduce_kernel<<<1, 256, 0, st>>>(buf, (int)count, c->nranks, c->rank, c->p2p.peers, c->p2p.ctr);
+        FEMOL_LAUNCH_CHECK();
+        ++c->p2p.n_red;
+        return FEMOL_OK;
+    }
     NCCL_CHECK(g_nccl.AllReduce(buf, buf, (size_t)count, ncclDouble_, ncclSum_, c->comm, st));
     return FEMOL_OK;
+}
+
+// out[0..total) = concatenation over ranks of their pieces (src: count doubles, stored at offset goff); the pieces
+// tile [0, total).  P2P pushes when the transport is attached, else a zero-padded all-reduce.
+int femol_dist_allgather(femol_comm* c, const double* src, int64_t count, int64_t goff, int64_t total, double* out, cudaStream_t st) {
+    if (c->p2p.on && (size_t)total <= c->p2p.gather_doubles && ((count | goff | total) & 1) == 0) {
+        int64_t blocks = (total / 2 + 255) / 256;
+        if (blocks > 32) blocks = 32;
+        if (blocks < 1) blocks = 1;
+        p2p_gather_kernel<<<(int)blocks, 256, 0, st>>>(src, count, goff, total, out, c->nranks, c->rank, c->p2p.peers, c->p2p.off_gather,
+                                                       c->p2p.gather_doubles, c->p2p.ctr);
+        FEMOL_LAUNCH_CHECK();
+        ++c->p2p.n_gather;
+        return FEMOL_OK;
+    }
+    FEMOL_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)total * sizeof(double), st));
+    FEMOL_CUDA_CHECK(cudaMemcpyAsync(out + goff, src, (size_t)count * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return femol_dist_allreduce(c, out, total, st);
+}
+
+// ---- window set-up -------------------------------------------------------------------------------------------------
+// 1. every rank: femol_dist_p2p_open -> its 64-byte IPC handle;  2. the host all-gathers the handles (torch.distributed);
+// 3. every rank: femol_dist_p2p_attach(all handles); 4. a host barrier before the first transfer.
+extern "C" int femol_dist_p2p_open(femol_comm* c, int64_t halo_doubles, int64_t gather_doubles, void* h_handle64) {
+    FEMOL_REQUIRE(c && h_handle64 && halo_doubles >= 0 && gather_doubles >= 0, "femol_dist_p2p_open: bad argument");
+    FEMOL_REQUIRE(!c->p2p.win, "femol_dist_p2p_open: window already open");
+    FEMOL_REQUIRE(c->nranks <= P2P_MAX_RANKS, "femol_dist_p2p_open: too many ranks");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    femol_p2p& w = c->p2p;
+    w.halo_doubles = (size_t)((halo_doubles + 31) & ~31LL);
+    w.gather_doubles = (size_t)((gather_doubles + 31) & ~31LL);
+    w.off_gather = P2P_OFF_HALO + 4 * w.halo_doubles * sizeof(double);
+    w.win_bytes = w.off_gather + 2 * w.gather_doubles * sizeof(double);
+    FEMOL_CUDA_CHECK(cudaMalloc(&w.win, w.win_bytes));
+    FEMOL_CUDA_CHECK(cudaMemset(w.win, 0, w.win_bytes));
+    FEMOL_CUDA_CHECK(cudaMalloc(&w.ctr, P2P_C_N * sizeof(unsigned long long)));
+    FEMOL_CUDA_CHECK(cudaMemset(w.ctr, 0, P2P_C_N * sizeof(unsigned long long)));
+    cudaIpcMemHandle_t h;
+    FEMOL_CUDA_CHECK(cudaIpcGetMemHandle(&h, w.win));
+    memcpy(h_handle64, &h, sizeof(h));
+    FEMOL_CUDA_CHECK(cudaDeviceSynchronize());
+    return FEMOL_OK;
+}
+
+extern "C" int femol_dist_p2p_attach(femol_comm* c, const void* h_handles) {
+    FEMOL_REQUIRE(c && h_handles && c->p2p.win, "femol_dist_p2p_attach: open the window first");
+    femol_p2p& w = c->p2p;
+    for (int r = 0; r < c->nranks; ++r) {
+        if (r == c->rank) { w.peers.w[r] = w.win; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)h_handles + 64 * (size_t)r, sizeof(h));
+        void* ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            femol_set_error("femol_dist_p2p_attach: cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e));
+            cudaGetLastError();
+            return FEMOL_E_CUDA;
+        }
+        w.peers.w[r] = (char*)ptr;
+    }
+    w.on = true;
+    return FEMOL_OK;
+}
+
+// 0 = healthy; 1 = a wait timed out (peer lost); h_stats (optional, 3 values): halo / reduce / gather kernels launched
+extern "C" int femol_dist_p2p_status(femol_comm* c, int64_t* h_stats) {
+    FEMOL_REQUIRE(c, "femol_dist_p2p_status: null communicator");
+    if (h_stats) { h_stats[0] = c->p2p.n_halo; h_stats[1] = c->p2p.n_red; h_stats[2] = c->p2p.n_gather; }
+    if (!c->p2p.on) return 0;
+    unsigned long long err = 0;
+    FEMOL_CUDA_CHECK(cudaMemcpy(&err, c->p2p.ctr + P2P_C_ERR, sizeof(err), cudaMemcpyDeviceToHost));
+    return err ? 1 : 0;
 }
 
 extern "C" int femol_dist_allreduce_sum(femol_comm* c, double* buf, int64_t count, void* stream) {
@@ -478,6 +730,7 @@ dg_direction(int64_t n, const double* __restrict__ z, double* __restrict__ p, co
 
 bool femol_gmg_first_sweep(femol_gmg* g, const double** dinv, double* omega);
 int femol_gmg_iteration_hint(femol_gmg* g, int set);
+extern "C" int femol_dist_p2p_status(femol_comm* c, int64_t* h_stats);
 
 extern "C" int64_t femol_pcg_gmg_dist_workspace_doubles(femol_plan_t p) {
     if (!p) return 0;
@@ -486,13 +739,9 @@ extern "C" int64_t femol_pcg_gmg_dist_workspace_doubles(femol_plan_t p) {
 
 // K u = f on the strip partition with the distributed V-cycle as preconditioner.  plan / vals / f / u are the LOCAL
 // arrays of the rank's strip (all local rows; u and the result are valid on owned rows, ghost rows of u are refreshed).
-extern "C" int femol_pcg_gmg_dist(femol_plan_t plan, femol_gmg* gmg, const double* vals, const double* f, double* u, double rtol,
-                                  int max_iter, double* ws, int* h_iters, double* h_relres, void* stream) {
-    FEMOL_REQUIRE(plan && gmg && vals && f && u && ws, "femol_pcg_gmg_dist: null argument");
-    FEMOL_REQUIRE(rtol > 0.0 && max_iter >= 0, "femol_pcg_gmg_dist: bad tolerance / iteration limit");
-    FEMOL_REQUIRE(femol_gmg_is_dist(gmg), "femol_pcg_gmg_dist: the hierarchy is not distributed (femol_gmg_set_dist)");
-    FEMOL_REQUIRE(plan->ndof == 2 || plan->ndof == 6, "femol_pcg_gmg_dist: ndof must be 2 or 6");
-    cudaStream_t st = (cudaStream_t)stream;
+namespace {
+int pcg_gmg_dist_run(femol_plan_t plan, femol_gmg* gmg, const double* vals, const double* f, double* u, double rtol,
+                     int max_iter, double* ws, int* h_iters, double* h_relres, cudaStream_t st, cudaGraphExec_t& exec) {
     femol_comm* c = femol_gmg_dist_comm(gmg);
     const femol_strip s = *femol_gmg_dist_strip(gmg, 0);
     const int nd = plan->ndof;
@@ -533,6 +782,21 @@ extern "C" int femol_pcg_gmg_dist(femol_plan_t plan, femol_gmg* gmg, const doubl
         FEMOL_LAUNCH_CHECK();
         return FEMOL_OK;
     };
+    auto iteration = [&]() -> int {
+        if ((rc = femol_dist_exchange(c, p, nd, s, st)) != FEMOL_OK) return rc;
+        if ((rc = femol_apply_launch(plan, vals, p, q, nullptr, nullptr, nullptr, st)) != FEMOL_OK) return rc;
+        dg_dot<<<vgrid, DT, 0, st>>>(n_own, p + off, q + off, sc + G_PQ, red);
+        FEMOL_LAUNCH_CHECK();
+        if ((rc = femol_dist_allreduce(c, sc + G_PQ, 1, st)) != FEMOL_OK) return rc;
+        const double* dv = first_sweep ? dinv0 + s.own_lo * s.row_nodes * nd * nd : nullptr;
+        if (nd == 2) dg_update<2><<<ngrid, DT, 0, st>>>(n_own_nodes, p + off, q + off, u + off, r + off, sc, red, dv, omega0, z + off);
+        else dg_update<6><<<ngrid, DT, 0, st>>>(n_own_nodes, p + off, q + off, u + off, r + off, sc, red, dv, omega0, z + off);
+        FEMOL_LAUNCH_CHECK();
+        if ((rc = femol_gmg_dist_vcycle(gmg, r, z, st, first_sweep)) != FEMOL_OK) return rc;
+        return rz_and_direction(0);
+    };
+    bool use_graph = getenv("FEMOL_NO_GRAPH") == nullptr && femol_comm_size(c) > 0;
+    long long graph_kernels = 0;
     for (int restart = 0; restart < 6; ++restart) {
         if ((rc = true_residual(restart)) != FEMOL_OK) return rc;
         if (h_sc[G_FF] == 0.0) {  // zero right-hand side (global norm): the solution is zero whatever the warm start was
@@ -546,6 +810,20 @@ extern "C" int femol_pcg_gmg_dist(femol_plan_t plan, femol_gmg* gmg, const doubl
         if (total_iters >= max_iter) break;
         if ((rc = femol_gmg_dist_vcycle(gmg, r, z, st, false)) != FEMOL_OK) return rc;
         if ((rc = rz_and_direction(1)) != FEMOL_OK) return rc;
+        if (use_graph && !exec) {   // one CG iteration (static launch sequence: device-side scalars and epochs) -> CUDA graph
+            cudaGraph_t graph = nullptr;
+            const long long before = femol_launch_count(0);
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int crc = iteration();
+                graph_kernels = femol_launch_count(0) - before;
+                femol_count_launches(-graph_kernels);
+                const cudaError_t e = cudaStreamEndCapture(st, &graph);
+                if (crc != FEMOL_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
+                if (graph) cudaGraphDestroy(graph);
+            }
+            cudaGetLastError();
+            if (!exec) use_graph = false;
+        }
         bool finished = false;
         int first_batch = restart == 0 ? femol_gmg_iteration_hint(gmg, -1) - 3 : batch;
         while (!finished && total_iters < max_iter) {
@@ -553,20 +831,15 @@ extern "C" int femol_pcg_gmg_dist(femol_plan_t plan, femol_gmg* gmg, const doubl
             first_batch = 0;
             if (nb > max_iter - total_iters) nb = max_iter - total_iters;
             for (int it = 0; it < nb; ++it) {      // every rank enqueues the same sequence, converged or not
-                if ((rc = femol_dist_exchange(c, p, nd, s, st)) != FEMOL_OK) return rc;
-                if ((rc = femol_apply_launch(plan, vals, p, q, nullptr, nullptr, nullptr, st)) != FEMOL_OK) return rc;
-                dg_dot<<<vgrid, DT, 0, st>>>(n_own, p + off, q + off, sc + G_PQ, red);
-                FEMOL_LAUNCH_CHECK();
-                if ((rc = femol_dist_allreduce(c, sc + G_PQ, 1, st)) != FEMOL_OK) return rc;
-                const double* dv = first_sweep ? dinv0 + s.own_lo * s.row_nodes * nd * nd : nullptr;
-                if (nd == 2) dg_update<2><<<ngrid, DT, 0, st>>>(n_own_nodes, p + off, q + off, u + off, r + off, sc, red, dv, omega0, z + off);
-                else dg_update<6><<<ngrid, DT, 0, st>>>(n_own_nodes, p + off, q + off, u + off, r + off, sc, red, dv, omega0, z + off);
-                FEMOL_LAUNCH_CHECK();
-                if ((rc = femol_gmg_dist_vcycle(gmg, r, z, st, first_sweep)) != FEMOL_OK) return rc;
-                if ((rc = rz_and_direction(0)) != FEMOL_OK) return rc;
+                if (exec) { FEMOL_CUDA_CHECK(cudaGraphLaunch(exec, st)); femol_count_launches(graph_kernels); }
+                else if ((rc = iteration()) != FEMOL_OK) return rc;
             }
             FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
             FEMOL_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (femol_dist_p2p_status(c, nullptr) != 0) {
+                femol_set_error("femol_pcg_gmg_dist: a peer-memory wait timed out (a rank of the job is gone)");
+                return FEMOL_E_CUDA;
+            }
             total_iters = (int)h_sc[G_ITER];
             if (h_sc[G_DONE] == 2.0) { status = FEMOL_S_BREAKDOWN; finished = true; }
             else if (h_sc[G_DONE] == 1.0) finished = true;
@@ -583,4 +856,29 @@ extern "C" int femol_pcg_gmg_dist(femol_plan_t plan, femol_gmg* gmg, const doubl
     if (h_iters) *h_iters = total_iters;
     if (h_relres) *h_relres = true_rel;
     return status;
+}
+}  // namespace
+
+extern "C" int femol_pcg_gmg_dist(femol_plan_t plan, femol_gmg* gmg, const double* vals, const double* f, double* u, double rtol,
+                                  int max_iter, double* ws, int* h_iters, double* h_relres, void* stream) {
+    FEMOL_REQUIRE(plan && gmg && vals && f && u && ws, "femol_pcg_gmg_dist: null argument");
+    FEMOL_REQUIRE(rtol > 0.0 && max_iter >= 0, "femol_pcg_gmg_dist: bad tolerance / iteration limit");
+    FEMOL_REQUIRE(femol_gmg_is_dist(gmg), "femol_pcg_gmg_dist: the hierarchy is not distributed (femol_gmg_set_dist)");
+    FEMOL_REQUIRE(plan->ndof == 2 || plan->ndof == 6, "femol_pcg_gmg_dist: ndof must be 2 or 6");
+    // stream capture is not permitted on the legacy default stream: run on the library's side stream (as femol_pcg_gmg)
+    cudaStream_t user = (cudaStream_t)stream, st = user;
+    bool forked = false;
+    if (getenv("FEMOL_NO_GRAPH") == nullptr && femol_stream_is_default(user)) {
+        int frc = femol_stream_fork(user, &st);
+        if (frc != FEMOL_OK) return frc;
+        forked = true;
+    }
+    cudaGraphExec_t exec = nullptr;
+    int rc = pcg_gmg_dist_run(plan, gmg, vals, f, u, rtol, max_iter, ws, h_iters, h_relres, st, exec);
+    if (exec) cudaGraphExecDestroy(exec);
+    if (forked) {
+        const int jrc = femol_stream_join(st, user);
+        if (rc >= 0 && jrc != FEMOL_OK) rc = jrc;
+    }
+    return rc;
 }

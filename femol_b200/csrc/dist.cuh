@@ -27,6 +27,8 @@ int femol_comm_size(const femol_comm* c);
 int femol_dist_exchange(femol_comm* c, double* x, int width, const femol_strip& s, cudaStream_t st);
 // buf[0..count) = sum over ranks, in place, in stream order (deterministic: same result on every rank)
 int femol_dist_allreduce(femol_comm* c, double* buf, int64_t count, cudaStream_t st);
+// out[0..total) = the ranks' pieces side by side (mine: src[0..count) at offset goff); the pieces tile [0, total)
+int femol_dist_allgather(femol_comm* c, const double* src, int64_t count, int64_t goff, int64_t total, double* out, cudaStream_t st);
 
 // ---- distributed multigrid entry points of gmg.cu used by the distributed PCG (dist.cu) ---------------------------
 struct femol_gmg;

@@ -1108,8 +1108,10 @@ int vcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, boo
                                               (const int32_t*)L.lat_node));
             femol_count_launch();
             // level 0 inside CG: the last kernel of the V-cycle also delivers r . z
-            const femol_epilogue jac = {FEMOL_EPI_JACOBI, r, L.dinv, g->omega, rz_out, red_ws};
-            if (rz_out && rz_fused) *rz_fused = true;
+            // (the single-precision product has no fused dot: with a float copy of level 0 the caller computes r . z)
+            const bool fuse_rz = rz_out && !L.vals32;
+            const femol_epilogue jac = {FEMOL_EPI_JACOBI, r, L.dinv, g->omega, fuse_rz ? rz_out : nullptr, fuse_rz ? red_ws : nullptr};
+            if (fuse_rz && rz_fused) *rz_fused = true;
             return L.vals32 ? femol_spmv_f32_epilogue_launch(L.plan, L.vals32, L.t, e, jac, st)
                             : femol_apply_epilogue_launch(L.plan, L.vals, L.t, e, jac, st);
         }
@@ -1199,6 +1201,7 @@ extern "C" int femol_gmg_destroy(femol_gmg* g) {
             femol_plan_destroy(L.plan);
             cudaFree(L.fixed); cudaFree(L.ke); cudaFree(L.vals); cudaFree(L.vals32); cudaFree(L.r); cudaFree(L.e); cudaFree(L.r2); cudaFree(L.e2);
         }
+        else cudaFree(L.vals32);
         cudaFree(L.dinv); cudaFree(L.t);
     }
     cudaFree(g->coarse_inv);
@@ -1289,6 +1292,12 @@ int gmg_create_impl(int64_t nx, int64_t ny, int ndof, femol_plan_t fine_plan, co
                 GCHECK(cudaMemcpyAsync(g->node_lat, lat->node_lat, L.n_nodes * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
                 GCHECK(cudaMemcpyAsync(g->child_ptr, lat->child_ptr, (nec + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
                 GCHECK(cudaMemcpyAsync(g->child_idx, lat->child_idx, fine_plan->n_elem * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+                // Level 0 of a lattice hierarchy is an assembled CSR operator (no stencil): the two products of the V-cycle
+                // (residual, post-smoothing) read a single-precision copy like the coarse levels do - 12 -> 8 bytes per
+                // node-block entry pair, and on T6 meshes these two products are 2/3 of a CG iteration.  CG's own product
+                // K p and the residual it converges on stay FP64.  FEMOL_GMG_F32_FINE=0 switches the copy off.
+                const char* ef = getenv("FEMOL_GMG_F32_FINE");
+                if (g->f32_levels && ndof == 2 && !(ef && atoi(ef) == 0)) GCHECK(cudaMalloc(&L.vals32, fine_plan->nnz * sizeof(float)));
             }
         } else {
             Level& F = g->lv[l - 1];
@@ -1415,6 +1424,10 @@ int gmg_setup_impl(femol_gmg* g, const double* e_base, int base_pe, const double
                    const double* fine_vals, cudaStream_t st) {
     const int nd = g->nd;
     g->lv[0].vals = const_cast<double*>(fine_vals);
+    if (g->lv[0].vals32) {
+        int rc = femol_to_f32_launch(g->lv[0].plan, fine_vals, g->lv[0].vals32, st);
+        if (rc != FEMOL_OK) return rc;
+    }
     const char* env_old = getenv("FEMOL_GMG_OLD_COARSEN");
     const bool fast_coarsen = !(env_old && atoi(env_old) != 0);
     for (int l = 1; l < g->n_levels; ++l) {
@@ -1586,6 +1599,19 @@ extern "C" int femol_gmg_dist_refresh(femol_gmg* g, void* stream) {
     return gmg_setup_impl(d->coarse, d->gke, 1, nullptr, 0, nullptr, d->gvals, st);
 }
 
+// h_out[0] = doubles of the largest halo message, h_out[1] = doubles of the gathered level (window sizes of the P2P transport)
+extern "C" int femol_gmg_dist_p2p_sizes(femol_gmg* g, int64_t* h_out) {
+    FEMOL_REQUIRE(g && g->dist && h_out, "femol_gmg_dist_p2p_sizes: not a distributed hierarchy");
+    int64_t halo = 0;
+    for (int l = 0; l < g->dist->n_dist; ++l) {
+        const femol_strip& s = g->dist->strip[l];
+        const int64_t rows = s.h_up > s.h_down ? s.h_up : s.h_down;
+        if (rows * s.row_nodes * g->nd > halo) halo = rows * s.row_nodes * g->nd;
+    }
+    h_out[0] = halo; h_out[1] = g->dist->coarse->lv[0].n;
+    return FEMOL_OK;
+}
+
 extern "C" int femol_gmg_dist_exchange(femol_gmg* g, int level, double* x, int width, void* stream) {
     FEMOL_REQUIRE(g && g->dist && x && level >= 0 && level <= g->dist->n_dist && width >= 1, "femol_gmg_dist_exchange: bad argument");
     return femol_dist_exchange(g->dist->comm, x, width, g->dist->strip[level], (cudaStream_t)stream);
@@ -1600,10 +1626,7 @@ int dist_gather_solve(femol_gmg* g, cudaStream_t st) {
     const femol_strip& s = d->strip[d->n_dist];
     const int64_t rowd = s.row_nodes * ND;
     const int64_t gn = d->coarse->lv[0].n;
-    FEMOL_CUDA_CHECK(cudaMemsetAsync(d->gr, 0, (size_t)gn * sizeof(double), st));
-    FEMOL_CUDA_CHECK(cudaMemcpyAsync(d->gr + (s.row0 + s.own_lo) * rowd, L.r + s.own_lo * rowd,
-                                     (size_t)(s.own_hi - s.own_lo) * rowd * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    int rc = femol_dist_allreduce(d->comm, d->gr, gn, st);
+    int rc = femol_dist_allgather(d->comm, L.r + s.own_lo * rowd, (s.own_hi - s.own_lo) * rowd, (s.row0 + s.own_lo) * rowd, gn, d->gr, st);
     if (rc != FEMOL_OK) return rc;
     rc = vcycle<ND>(d->coarse, 0, d->gr, d->ge, st, false);
     if (rc != FEMOL_OK) return rc;
@@ -1642,15 +1665,15 @@ int dvcycle(femol_gmg* g, int l, const double* r, double* e, cudaStream_t st, bo
         FEMOL_CUDA_CHECK(femol_launch_pdl(prolong_add_kernel<ND>, dim3(grid_for(L.n_nodes)), dim3(256), 0, st, L.nx, L.ny, C.nx,
                                           (const uint8_t*)L.fixed, (const double*)C.e, (const double*)e, L.t, (const int32_t*)L.lat_node));
         femol_count_launch();
-        if ((rc = femol_dist_exchange(d->comm, L.t, ND, s, st)) != FEMOL_OK) return rc;
+        // no exchange here: the prolongation is computed on every local row, and on the halo rows both of its inputs are
+        // valid (e since the exchange before the residual product, e_c since the exchange above / the replicated solve)
         const femol_epilogue jac = {FEMOL_EPI_JACOBI, r, L.dinv, g->omega, nullptr, nullptr};
         return L.vals32 ? femol_spmv_f32_epilogue_launch(L.plan, L.vals32, L.t, e, jac, st)
                         : femol_apply_epilogue_launch(L.plan, L.vals, L.t, e, jac, st);
     }
     prolong_add_kernel<ND><<<grid_for(L.n_nodes), 256, 0, st>>>(L.nx, L.ny, C.nx, L.fixed, C.e, e, e, L.lat_node);
     FEMOL_LAUNCH_CHECK();
-    if ((rc = femol_dist_exchange(d->comm, e, ND, s, st)) != FEMOL_OK) return rc;
-    return smooth<ND>(g, l, r, e, false, st);
+    return smooth<ND>(g, l, r, e, false, st);      // (halo rows of e + P e_c are valid: see above)
 }
 
 }  // namespace

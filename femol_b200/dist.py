@@ -15,6 +15,7 @@ The index bookkeeping below (`Partition`) is pure host logic and is tested on CP
 (tests/test_dist.py), where numpy/scipy stand in for the device kernels.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -332,6 +333,37 @@ def owned_gather_index(own_global, n_total, world):
     return m, np.concatenate(_gather_objects(pad, world))
 
 
+def attach_p2p(F, comm, gmg, world):
+    """Open this rank's peer-memory window, swap the CUDA IPC handles through torch.distributed and map the peers'
+    windows (femol_dist_p2p_open / _attach).  Returns 'p2p', or 'nccl' when some rank could not map a peer (the
+    library then keeps using NCCL send/recv; all ranks take the same decision)."""
+    import torch
+    import torch.distributed as dist
+    L = F._lib
+    sizes = (ctypes.c_int64 * 2)()
+    L.call('femol_gmg_dist_p2p_sizes', gmg, sizes)
+    handle = (ctypes.c_char * 64)()
+    ok = 1
+    try:
+        L.call('femol_dist_p2p_open', comm, int(sizes[0]), int(sizes[1]), handle)
+    except L.FemolError:
+        ok = 0
+    handles = _gather_objects((ok, bytes(handle)), world)
+    if not all(h[0] for h in handles):
+        return 'nccl'
+    blob = ctypes.create_string_buffer(b''.join(h[1] for h in handles), 64 * world)
+    try:
+        L.call('femol_dist_p2p_attach', comm, blob)
+    except L.FemolError:
+        ok = 0
+    oks = _gather_objects(ok, world)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if not all(oks):
+        raise L.FemolError('peer-memory transport: some ranks attached and some did not; set FEMOL_DIST_TRANSPORT=nccl')
+    return 'p2p'
+
+
 def _dev_i64(values):
     return (ctypes.c_int64 * len(values))(*[int(v) for v in values])
 
@@ -445,6 +477,7 @@ class DistributedSIMP_COMP(object):
         self.solver_info = {}
         self.iteration_log = []
         self.loop, self.change, self.c = 0, 1.0, None
+        self.debug_timing, self.timing, self._t_last = False, {}, 0.0
         self._global_mask_lat = self._global_fixed_mask(lat_node)
 
     # ---- set-up helpers ---------------------------------------------------------------------------------------
@@ -501,6 +534,9 @@ class DistributedSIMP_COMP(object):
                (ctypes.c_int * len(lv))(*[v['h_up'] for v in lv]), (ctypes.c_int * len(lv))(*[v['h_down'] for v in lv]),
                ch, cplan, L.ptr(self._c_mask))
         self._gmg = g
+        self.transport = 'nccl'
+        if self.world > 1 and os.environ.get('FEMOL_DIST_TRANSPORT', 'p2p') != 'nccl':
+            self.transport = attach_p2p(F, self.comm, g, self.world)
 
     def __del__(self):
         try:
@@ -513,24 +549,43 @@ class DistributedSIMP_COMP(object):
             pass
 
     # ---- one SIMP iteration ----------------------------------------------------------------------------------------
+    def _tick(self, name):
+        """debug_timing: host wall time per section, with a device synchronisation at every boundary"""
+        if self.debug_timing:
+            import time
+            if self.debug_timing != 'host':
+                self.torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.timing[name] = self.timing.get(name, 0.0) + now - self._t_last
+            self._t_last = now
+
     def solve_displacement(self):
         """Assemble K(x^p) on the strip, refresh both hierarchies, distributed multigrid PCG -> local U (device)."""
         torch, L = self.torch, self.F_mod._lib
         lp = self.local_problem
         d = lp.device
+        if self.debug_timing:
+            import time
+            torch.cuda.synchronize()
+            self._t_last = time.perf_counter()
         torch.index_select(self._x, 0, self._loc_elems, out=self._x_loc)
+        self._tick('select')
         lp.assemble('K', X=self._x_loc, p=self.p)
+        self._tick('assemble')
         if self._gmg is None:
             self._build_hierarchy()
         else:
             lp._gmg_ready()
+        self._tick('gmg_local')
         L.call('femol_gmg_dist_refresh', self._gmg, L.stream())
+        self._tick('gmg_refresh')
         if self._ws is None:
             self._ws = torch.empty(int(L.load().femol_pcg_gmg_dist_workspace_doubles(d.plan)), dtype=torch.float64, device=d.dev)
         iters, relres = ctypes.c_int(0), ctypes.c_double(0.0)
         rc = L.call('femol_pcg_gmg_dist', d.plan, self._gmg, L.ptr(lp._Kv), L.ptr(lp._F_dev), L.ptr(self._U),
                     float(lp.solver_rtol), int(lp.solver_max_iter), L.ptr(self._ws), ctypes.byref(iters), ctypes.byref(relres),
                     L.stream())
+        self._tick('pcg')
         converged = rc == 0 or (rc == L.S_STAGNATED and relres.value <= lp.stagnation_bound)
         self.solver_info = {'iterations': iters.value, 'relres': relres.value, 'status': rc, 'converged': converged,
                             'preconditioner': 'gmg-dist'}
@@ -544,6 +599,7 @@ class DistributedSIMP_COMP(object):
     def iterate(self):
         torch, L = self.torch, self.F_mod._lib
         import torch.distributed as dist
+        from . import TOM_SIMP
         lp = self.local_problem
         d = lp.device
         self.solve_displacement()
@@ -556,20 +612,21 @@ class DistributedSIMP_COMP(object):
         n_own = dc_own.shape[0]
         self._send[:n_own] = dc_own
         c_loc = -(dc_own * self._x_loc[self._own_local]).sum() / float(self.p)
+        self._tick('sens')
         if self.world > 1:
             dist.all_gather_into_tensor(self._recv, self._send)
             dist.all_reduce(c_loc)
         else:
             self._recv.copy_(self._send)
         self._dc_pad[self._gather_index] = self._recv
-        self._dc.copy_(self._dc_pad[:self.n_elem])
         self._scal[0] = c_loc
-        from . import TOM_SIMP
-        TOM_SIMP.apply_filter(self._filter, self._x, self._dc, self._dcf)
+        self._tick('gather')
+        TOM_SIMP.apply_filter(self._filter, self._x, self._dc_pad, self._dcf)
         L.call('femol_oc_update', self.n_elem, L.ptr(self._x), L.ptr(self._dcf), 0, float(self.f), None, L.ptr(self._mask),
                L.ptr(self._xn), self._scal.data_ptr() + 4 * 8, L.ptr(self._red_ws), L.stream())
         self._x, self._xn = self._xn, self._x
         s = self._scal.cpu().numpy()
+        self._tick('filter_oc')
         self.c, self.change = float(s[0]), float(s[4])
         return self.change, self.c
 

@@ -33,6 +33,36 @@ def build_problem(F, kind, nx, ny, model='plane'):
     return gp
 
 
+def kernel_profile(opt, steps, rank):
+    from torch.profiler import profile, ProfilerActivity
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(steps):
+            opt.iterate()
+        torch.cuda.synchronize()
+    if rank != 0:
+        return
+    ev = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events() if e.device_type.name != 'CPU'),
+                key=lambda t: t[0])
+    span = ev[-1][1] - ev[0][0]
+    busy, cur_end = 0.0, ev[0][0]
+    for a_, b_, _ in ev:
+        if b_ > cur_end:
+            busy += b_ - max(a_, cur_end)
+            cur_end = b_
+    print('PROFILE span %.3f ms/step, device busy %.3f ms/step, pcg %s' % (span / 1e3 / steps, busy / 1e3 / steps, opt.solver_info))
+    gaps = sorted(((max(0.0, b[0] - a[1]), b[2]) for a, b in zip(ev[:-1], ev[1:])), reverse=True)
+    for g, n in gaps[:10]:
+        print('PROFILE    gap %8.1f us before %s' % (g, n[:100]))
+    per = {}
+    for a_, b_, name in ev:
+        d = per.setdefault(name[:110], [0.0, 0])
+        d[0] += b_ - a_; d[1] += 1
+    tot = sum(v[0] for v in per.values())
+    for name, (t, c) in sorted(per.items(), key=lambda kv: -kv[1][0])[:32]:
+        print('PROFILE %9.1f us/step %5.1f%% %7.1f launches/step %8.1f us/launch  %s' % (t / steps, 100 * t / tot, c / steps, t / c, name))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--mesh', default='q4')
@@ -44,6 +74,7 @@ def main():
     ap.add_argument('--rtol', type=float, default=1e-9)
     ap.add_argument('--no-reference', action='store_true', help='skip the single-GPU run (large meshes)')
     ap.add_argument('--out', default=None)
+    ap.add_argument('--profile', type=int, default=0, help='profile this many extra iterations with CUPTI (rank 0 prints)')
     a = ap.parse_args()
     import femol_b200 as F
     from femol_b200 import dist as fd
@@ -68,9 +99,20 @@ def main():
         log.append({'c': c, 'change': change, 'pcg': opt.solver_info['iterations'], 'relres': opt.solver_info['relres'],
                     'status': opt.solver_info['status']})
     X = opt.density()
+    if a.profile:
+        kernel_profile(opt, a.profile, rank)
+        for mode in (True, 'host'):
+            opt.debug_timing, opt.timing = mode, {}
+            for _ in range(a.profile):
+                opt.iterate()
+            opt.debug_timing = False
+            if rank == 0:
+                print('PROFILE host sections (ms/step, %s): %s' % ('synchronised' if mode is True else 'host time only',
+                                                                  {k: round(1e3 * v / a.profile, 3) for k, v in opt.timing.items()}))
     res = {'mesh': a.mesh, 'model': a.model, 'nx': a.nx, 'ny': a.ny, 'world': world, 'n_dist': opt.part.n_dist, 'cuts': opt.part.cuts,
            'ndof': int(gp.mesh.N_nodes * gp.N_dof), 'setup_s': t_setup, 'iteration_s': times, 'log': log,
-           'gpu_mem_gb': torch.cuda.max_memory_allocated() / 1e9}
+           'gpu_mem_gb': torch.cuda.max_memory_allocated() / 1e9, 'transport': getattr(opt, 'transport', None),
+           'launches': int(F._lib.load().femol_launch_count(0))}
     ok = True
     if not a.no_reference and rank == 0:
         ref = build_problem(F, a.mesh, a.nx, a.ny, a.model)
