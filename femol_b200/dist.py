@@ -20,7 +20,7 @@ import os
 import numpy as np
 
 __all__ = ['shard_items', 'Partition', 'DistributedStatic', 'init_process_group', 'StripPartition', 'DistributedSIMP_COMP',
-           'create_comm', 'coarsen_mask_host', 'owned_gather_index']
+           'create_comm', 'coarsen_mask_host', 'owned_gather_index', 'strip_local_mesh', 'strip_halo_rows']
 
 
 def init_process_group(backend=None):
@@ -261,6 +261,51 @@ def coarsen_mask_host(mask, nx, ny):
     return np.ascontiguousarray(m[jj][:, ii]).reshape(-1), nxc, nyc
 
 
+def _node_rows(Nx, lat_node, n_nodes):
+    """(lattice index of every node or None = identity, lattice row of every node)"""
+    if lat_node is None:
+        return None, np.arange(n_nodes, dtype=np.int64) // (Nx + 1)
+    node_lat = np.empty(n_nodes, dtype=np.int64)
+    node_lat[lat_node] = np.arange(n_nodes, dtype=np.int64)
+    return node_lat, node_lat // (Nx + 1)
+
+
+def strip_halo_rows(cells, Nx, lat_node, n_nodes):
+    """Lattice rows an element spans (1: Q4 / T3 on their corner lattice, 2: T6) = rows a strip needs from below."""
+    _, node_row = _node_rows(Nx, lat_node, n_nodes)
+    r = node_row[np.asarray(cells)]
+    return int((r.max(axis=1) - r.min(axis=1)).max())
+
+
+def strip_local_mesh(cells, Nx, lat_node, n_nodes, part):
+    """Cut the strip of `part` out of a lattice mesh: every element whose nodes lie on the local rows [row0, top], nodes
+    renumbered in lattice order (local id = lattice index - row0 * (Nx + 1)).  Returns dict(elements: global element
+    ids (ascending), nodes: global node id of every local node, cells: local connectivity, owned: the elements whose
+    lowest row this rank owns - each element has exactly one owner).  Checks that every element with a node on an owned
+    row is local and stays inside the rows a halo exchange fills."""
+    cells = np.asarray(cells)
+    npx = Nx + 1
+    node_lat, node_row = _node_rows(Nx, lat_node, n_nodes)
+    cell_rows = node_row[cells]
+    rmin_e, rmax_e = cell_rows.min(axis=1), cell_rows.max(axis=1)
+    sel = (rmin_e >= part.row0) & (rmax_e <= part.top)
+    elements = np.nonzero(sel)[0]
+    lat0 = part.row0 * npx
+    g_nodes = np.arange(lat0, lat0 + (part.top - part.row0 + 1) * npx, dtype=np.int64)
+    if lat_node is not None:
+        g_nodes = np.asarray(lat_node, dtype=np.int64)[g_nodes]
+    lc = cells[elements]
+    lc = (lc if node_lat is None else node_lat[lc]) - lat0
+    own = (rmin_e[sel] >= part.own_begin) & (rmin_e[sel] < part.own_end)
+    lev0 = part.levels[0]
+    touch = (rmax_e >= part.own_begin) & (rmin_e <= part.own_end - 1)
+    lo_ok = part.own_begin - (lev0['h_up'] if part.rank > 0 else 0)
+    hi_ok = part.own_end - 1 + (lev0['h_down'] if part.rank < part.world - 1 else 0)
+    if not (sel[touch].all() and (rmin_e[touch] >= lo_ok).all() and (rmax_e[touch] <= hi_ok).all()):
+        raise ValueError('an element of an owned row reaches beyond the exchanged halo rows')
+    return {'elements': elements, 'nodes': g_nodes, 'cells': lc, 'owned': own}
+
+
 class StripPartition(object):
     """Strips of lattice rows for `world` ranks with `n_dist` distributed multigrid levels, seen from `rank`.
 
@@ -396,38 +441,14 @@ class DistributedSIMP_COMP(object):
         Nx, Ny, lat_node = _lattice_of(gp)
         self.Nx, self.Ny = Nx, Ny
         cells = np.asarray(gm.cells[ctype])
-        npx = Nx + 1
-        if lat_node is None:
-            node_row = np.arange(gm.N_nodes, dtype=np.int64) // npx
-            node_lat = None
-        else:
-            node_lat = np.empty(gm.N_nodes, dtype=np.int64)
-            node_lat[lat_node] = np.arange(gm.N_nodes, dtype=np.int64)
-            node_row = node_lat // npx
-        cell_rows = node_row[cells]
-        rmin_e, rmax_e = cell_rows.min(axis=1), cell_rows.max(axis=1)
-        h_up0 = int((rmax_e - rmin_e).max())
+        h_up0 = strip_halo_rows(cells, Nx, lat_node, gm.N_nodes)
         if n_dist is None:
             n_dist = StripPartition.pick_levels(Nx, Ny, self.world)
         part = self.part = StripPartition(Ny, self.rank, self.world, n_dist, h_up0=h_up0)
-        # ---- local mesh: lattice rows [row0, top], nodes renumbered in lattice order ------------------------
-        sel = (rmin_e >= part.row0) & (rmax_e <= part.top)
-        self.local_elements = np.nonzero(sel)[0]                       # global element ids, ascending
-        lat0 = part.row0 * npx
-        n_loc_nodes = (part.top - part.row0 + 1) * npx
-        g_nodes = np.arange(lat0, lat0 + n_loc_nodes, dtype=np.int64)
-        if lat_node is not None:
-            g_nodes = lat_node[g_nodes]
-        self.local_to_global = g_nodes
-        lc = cells[self.local_elements]
-        lc = (lc if node_lat is None else node_lat[lc]) - lat0
-        own = (rmin_e[sel] >= part.own_begin) & (rmin_e[sel] < part.own_end)     # element -> owner of its lowest row
-        # every element with a node on an owned row is local and stays inside the rows a halo exchange fills
-        touch = (rmax_e >= part.own_begin) & (rmin_e <= part.own_end - 1)
-        lo_ok = part.own_begin - (h_up0 if self.rank > 0 else 0)
-        hi_ok = part.own_end - 1 + (part.levels[0]['h_down'] if self.rank < self.world - 1 else 0)
-        assert sel[touch].all() and (rmin_e[touch] >= lo_ok).all() and (rmax_e[touch] <= hi_ok).all(), \
-            'an element of an owned row reaches beyond the exchanged halo rows'
+        cut = strip_local_mesh(cells, Nx, lat_node, gm.N_nodes, part)
+        self.local_elements, self.local_to_global = cut['elements'], cut['nodes']
+        g_nodes, lc, own = cut['nodes'], cut['cells'], cut['owned']
+        n_loc_nodes = g_nodes.shape[0]
         kw = {'quad_element': gm.ElementClasses['quad']} if ctype == 'quad' else {'tri_element': gm.ElementClasses['triangle']}
         lm = self.local_mesh = F.Mesh(gm.points[g_nodes], {ctype: lc}, structured=gm.structured, **kw)
         assert lm.N_nodes == n_loc_nodes, 'every local lattice node is used by a local element'

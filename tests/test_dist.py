@@ -236,3 +236,260 @@ def test_pcg_dist_two_gpus(nx, ny, model):
             if p.is_alive():
                 p.kill()
     assert len(results) == len(procs) and all(r[1] == 'ok' for r in results), results
+
+
+# =====================================================================================================================
+# Strip partition with multigrid (femol_b200/dist.py StripPartition / DistributedSIMP_COMP)
+# =====================================================================================================================
+@pytest.mark.parametrize('Ny,world,n_dist', [(2828, 8, 4), (48, 2, 2), (1000, 4, 5), (129, 3, 3), (17, 1, 2), (64, 2, 1)])
+def test_strip_partition_levels_coarsen_like_the_global_grid(Ny, world, n_dist):
+    from femol_b200.dist import StripPartition
+    parts = [StripPartition(Ny, r, world, n_dist) for r in range(world)]
+    A = 1 << n_dist
+    assert all(c % A == 0 for c in parts[0].cuts[1:-1]) and parts[0].cuts[0] == 0 and parts[0].cuts[-1] == Ny + 1
+    ny_g = Ny
+    for l in range(n_dist + 1):
+        ob = [p.levels[l]['own_begin'] for p in parts]
+        oe = [p.levels[l]['own_end'] for p in parts]
+        assert ob[0] == 0 and oe[-1] == ny_g + 1 and all(oe[i] == ob[i + 1] for i in range(world - 1))   # owned rows tile the level
+        for p in parts:
+            lev = p.levels[l]
+            assert lev['Ny'] == ny_g and lev['row0'] <= lev['own_begin'] < lev['own_end'] <= lev['top'] + 1
+            if p.rank > 0:
+                assert lev['own_begin'] - lev['row0'] >= lev['h_up']              # the exchanged rows exist locally
+            if p.rank < world - 1:
+                assert lev['top'] - (lev['own_end'] - 1) >= lev['h_down']
+            if l < n_dist:
+                nyl = lev['top'] - lev['row0']
+                nxt = p.levels[l + 1]
+                # ceil(n / 2) coarsening of the local grid lands on the local grid of the next level
+                assert lev['row0'] % 2 == 0 and lev['row0'] // 2 == nxt['row0']
+                assert (nyl + 1) // 2 == nxt['top'] - nxt['row0']
+                if p.rank < world - 1:
+                    assert nyl % 2 == 0                                           # no spurious trailing single cell
+        ny_g = (ny_g + 1) // 2
+
+
+def test_strip_partition_rejects_thin_strips():
+    from femol_b200.dist import StripPartition
+    with pytest.raises(ValueError):
+        StripPartition(30, 0, 4, 4)
+
+
+def test_coarsen_mask_host_matches_the_device_rule():
+    from femol_b200.dist import coarsen_mask_host
+    rng = np.random.default_rng(0)
+    for nx, ny in [(5, 6), (8, 4), (7, 7), (1, 3)]:
+        m = rng.integers(0, 4, size=(ny + 1) * (nx + 1)).astype(np.uint8)
+        out, nxc, nyc = coarsen_mask_host(m, nx, ny)
+        assert (nxc, nyc) == ((nx + 1) // 2, (ny + 1) // 2)
+        for J in range(nyc + 1):
+            for I in range(nxc + 1):            # csrc/gmg.cu coarsen_mask: coarse (I, J) sits on fine (min(2I, nx), min(2J, ny))
+                assert out[J * (nxc + 1) + I] == m[min(2 * J, ny) * (nx + 1) + min(2 * I, nx)]
+
+
+def _strip_worker(rank, world, port, kind, nx, ny, n_dist, out_q):
+    for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    import femol_oracle as o
+    import cases
+    from femol_b200 import dist as fd
+    from femol_b200 import mesh as fmesh
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        gm = {'q4': fmesh.rectangle_Q4, 't6': fmesh.rectangle_T6, 't3': fmesh.rectangle_T3}[kind](float(nx), float(ny), nx, ny)
+        ctype = gm.contains[0]
+        cells = np.asarray(gm.cells[ctype])
+        pts = gm.points[:, :2]
+        # lattice of the mesh (host logic of FEM_Problem.node_lattice, without a device)
+        hx = np.unique(np.round(pts[:, 0], 9)); hy = np.unique(np.round(pts[:, 1], 9))
+        Nx, Ny = hx.shape[0] - 1, hy.shape[0] - 1
+        li = np.rint(pts[:, 0] / (hx[1] - hx[0])).astype(np.int64); lj = np.rint(pts[:, 1] / (hy[1] - hy[0])).astype(np.int64)
+        lat = lj * (Nx + 1) + li
+        lat_node = np.empty(gm.N_nodes, dtype=np.int64); lat_node[lat] = np.arange(gm.N_nodes)
+        if kind == 'q4':
+            assert np.array_equal(lat_node, np.arange(gm.N_nodes))
+            lat_node = None
+        h_up0 = fd.strip_halo_rows(cells, Nx, lat_node, gm.N_nodes)
+        assert h_up0 == (2 if kind == 't6' else 1)
+        part = fd.StripPartition(Ny, rank, world, n_dist, h_up0=h_up0)
+        cut = fd.strip_local_mesh(cells, Nx, lat_node, gm.N_nodes, part)
+        g_nodes = cut['nodes']
+        # local connectivity = global connectivity in local numbering; local nodes in lattice order
+        assert np.array_equal(g_nodes[cut['cells']], cells[cut['elements']])
+        lp = pts[g_nodes]
+        assert np.all(np.diff(lp[:, 1].reshape(-1, Nx + 1)[:, 0]) > 0) and np.all(np.diff(lp[:Nx + 1, 0]) > 0)
+        # every element has exactly one owner; the all-gather index puts every owned value in its global slot
+        owned_global = cut['elements'][cut['owned']]
+        m, index = fd.owned_gather_index(owned_global, cells.shape[0], world)
+        send = torch.full((m,), -1.0, dtype=torch.float64)
+        send[:owned_global.shape[0]] = torch.from_numpy(owned_global.astype(np.float64))
+        recv = [torch.empty(m, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(recv, send)
+        full = torch.full((cells.shape[0] + 1,), -7.0, dtype=torch.float64)
+        full[torch.from_numpy(index)] = torch.cat(recv)
+        assert np.array_equal(full[:-1].numpy(), np.arange(cells.shape[0], dtype=np.float64))
+        # owned rows of the LOCAL matrix are the global rows (local assembly needs no communication)
+        nd = 2
+        etype = {'q4': 'Q4', 't6': 'T6', 't3': 'T3'}[kind]
+        arr = {'etype': etype, 'points': gm.points, 'cells': cells, 'ndof': nd, 'tensors': o.iso_tensors(1.0, 0.3, 1.0),
+               'coat_tensors': None, 'structured': False, 'fixed_idx': np.zeros(0, dtype=np.int64)}
+        X = cases.density_field(cells.shape[0])
+        Kg = o.global_matrices(arr, 'K', X, 3)
+        larr = dict(arr); larr['points'] = gm.points[g_nodes]; larr['cells'] = cut['cells']
+        Kl = o.global_matrices(larr, 'K', X[cut['elements']], 3)
+        npx = Nx + 1
+        lo, hi = (part.own_begin - part.row0) * npx, (part.own_end - part.row0) * npx
+        rows = (np.arange(lo, hi)[:, None] * nd + np.arange(nd)[None]).reshape(-1)
+        gidx = (g_nodes[:, None] * nd + np.arange(nd)[None]).reshape(-1)
+        ref = Kg[gidx[rows]][:, gidx]
+        assert abs(Kl[rows] - ref).max() < 1e-12 * abs(Kg).max()
+        # ... and they only reference owned nodes and the halo rows an exchange fills
+        lev = part.levels[0]
+        cols = np.unique(Kl[rows].tocoo().col // nd) // npx + part.row0
+        assert cols.min() >= part.own_begin - (lev['h_up'] if rank > 0 else 0)
+        assert cols.max() <= part.own_end - 1 + (lev['h_down'] if rank < world - 1 else 0)
+        out_q.put((rank, 'ok', 0))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        out_q.put((rank, 'fail: %s\n%s' % (e, traceback.format_exc()), -1))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,kind,nx,ny,n_dist', [(2, 'q4', 12, 16, 2), (2, 't6', 6, 8, 2), (3, 't3', 5, 24, 2)])
+def test_strip_local_mesh_gloo(world, kind, nx, ny, n_dist):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_strip_worker, args=(r, world, port, kind, nx, ny, n_dist, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, it in sorted(results):
+        assert status == 'ok', 'rank %d: %s' % (rank, status)
+
+
+# ---- DistributedSIMP_COMP on the device: one rank (always) and two ranks (boxes with 2 GPUs) -------------------------
+def _simp_problem(F, kind, nx, ny):
+    Lx, Ly = float(nx), float(ny)
+    mesh = {'q4': F.mesh.rectangle_Q4, 't3': F.mesh.rectangle_T3, 't6': F.mesh.rectangle_T6}[kind](Lx, Ly, nx, ny)
+    gp = F.FEM_Problem('displacement', 'plane', mesh)
+    gp.define_materials(F.materials.general_isotropic()); gp.define_tensors(1)
+    gp.add_fixed_domain(F.domains.inside_box([0], [[0, Ly]]), ddls=[0, 1])
+    gp.add_forces([0, -1.0], F.domains.inside_box([Lx], [[Ly / 2 - 1, Ly / 2 + 1]]))
+    gp.solver_rtol = 1e-10
+    return gp
+
+
+def _check_strip_simp(F, fd, kind, nx, ny, n_dist, comm, iters=3):
+    opt = fd.DistributedSIMP_COMP(F, _simp_problem(F, kind, nx, ny), comm, volfrac=0.4, penal=3, rmin=1.5, n_dist=n_dist)
+    log = []
+    for _ in range(iters):
+        opt.iterate()
+        log.append((opt.c, opt.solver_info['iterations'], opt.solver_info['converged']))
+    ref_p = _simp_problem(F, kind, nx, ny)
+    ref = F.SIMP_COMP(ref_p, volfrac=0.4, penal=3, rmin=1.5)
+    ref.archive = False
+    ref_log = []
+    for _ in range(iters):
+        ref.iterate()
+        ref_log.append((ref.c, ref_p.solver_info['iterations']))
+    assert all(l[2] for l in log), log
+    assert np.abs(opt.density() - ref.density()).max() < 1e-4                        # north star: densities within 1e-4
+    assert max(abs(a[0] - b[0]) / abs(b[0]) for a, b in zip(log, ref_log)) < 1e-6     # compliance within 1e-6
+    # the distributed V-cycle is the same operator: iteration counts differ by rounding only
+    assert max(abs(a[1] - b[1]) for a, b in zip(log, ref_log)) <= 1, (log, ref_log)
+    nodes, U = opt.owned_displacement()
+    U_ref = ref._U.view(-1, 2).cpu().numpy()[nodes]
+    assert np.abs(U - U_ref).max() < 1e-6 * np.abs(U_ref).max()
+    return opt
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('kind,nx,ny,n_dist', [('q4', 48, 40, 2), ('t6', 20, 24, 2), ('t3', 33, 21, 1)])
+def test_strip_simp_single_rank(kind, nx, ny, n_dist):
+    """One rank: the truncated strip hierarchy + the gathered, replicated coarse hierarchy reproduce SIMP_COMP."""
+    import femol_b200 as F
+    from femol_b200 import dist as fd
+    comm = fd.create_comm(F)
+    try:
+        opt = _check_strip_simp(F, fd, kind, nx, ny, n_dist, comm)
+        assert opt.part.cuts == [0, opt.Ny + 1]
+        del opt
+    finally:
+        F._lib.load().femol_dist_destroy(comm)
+
+
+def _gpu_strip_worker(rank, world, port, kind, nx, ny, n_dist, transport, out_q):
+    for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank), FEMOL_DIST_TRANSPORT=transport)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        import femol_b200 as F
+        from femol_b200 import dist as fd
+        comm = fd.create_comm(F)
+        opt = _check_strip_simp(F, fd, kind, nx, ny, n_dist, comm)
+        assert opt.transport == transport
+        stats = (ctypes_i64 * 3)()
+        assert F._lib.load().femol_dist_p2p_status(comm, stats) == 0
+        if transport == 'p2p':
+            assert stats[0] > 0 and stats[1] > 0 and stats[2] > 0          # halo / all-reduce / gather kernels ran
+        X = torch.from_numpy(opt.density()).cuda()
+        Xs = [torch.empty_like(X) for _ in range(world)]
+        dist.all_gather(Xs, X)
+        assert all(torch.equal(Xs[0], x) for x in Xs), 'replicated densities must be bit-identical on all ranks'
+        del opt
+        torch.cuda.synchronize()
+        dist.barrier()
+        F._lib.load().femol_dist_destroy(comm)
+        out_q.put((rank, 'ok', 0))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        out_q.put((rank, 'fail: %s\n%s' % (e, traceback.format_exc()), -1))
+    finally:
+        dist.destroy_process_group()
+
+
+import ctypes as _ctypes  # noqa: E402
+ctypes_i64 = _ctypes.c_int64
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('kind,nx,ny,n_dist,transport', [('q4', 48, 40, 2, 'p2p'), ('t6', 20, 24, 2, 'p2p'), ('q4', 40, 33, 1, 'nccl')])
+def test_strip_simp_two_gpus(kind, nx, ny, n_dist, transport):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gpu_strip_worker, args=(r, 2, port, kind, nx, ny, n_dist, transport, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = []
+    try:
+        for _ in procs:
+            results.append(q.get(timeout=200))
+            if results[-1][1] != 'ok':
+                break
+    finally:
+        for p in procs:
+            p.join(timeout=5 if (results and results[-1][1] != 'ok') else 60)
+            if p.is_alive():
+                p.kill()
+    assert len(results) == len(procs) and all(r[1] == 'ok' for r in results), results
