@@ -11,7 +11,8 @@ is warm-started from the previous displacement, as any SIMP driver would).
   e2e    the same step through the public API with HOST buffers: pinned-host densities copied in, new
          densities + (change, objective) copied out, every step, inside the timed region.
   N > 1  independent designs sharded one per GPU (north-star "design batches"): no data-path collective,
-         weak scaling; time = max over ranks.
+         weak scaling; time = max over ranks.  A second leg (`partitioned` in the JSON line) runs ONE T6 problem
+         strip-partitioned over all N GPUs (strong scaling) next to the same problem on one GPU.
   --impl reference   the CPU oracle port (vectorised numpy/scipy restatement of the reference algorithm; the
          reference itself is pure Python and cannot travel to the GPU box) on a bounded sample mesh.
 """
@@ -44,6 +45,7 @@ def parse():
     ap.add_argument('--sample-ny', type=int, default=200)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-procs', type=int, default=None, help='CPU legs: parallel design replicas (default: every host core, at most 64)')
+    ap.add_argument('--part-n', type=int, default=1414, help='N > 1: T6 mesh (n x n elements) of the strip-partitioned leg; 0 = skip')
     return ap.parse_args()
 
 
@@ -194,6 +196,97 @@ def build_gpu_problem(F, nx, ny, rtol, precond):
     opt = F.SIMP_COMP(problem, volfrac=0.4, penal=3, rmin=1.5)
     opt.archive = False
     return problem, opt
+
+
+def run_partitioned(F, args, rank, world):
+    """N > 1, second leg (north star: "for large meshes, work is partitioned across 2, 4 and 8 GPUs ... with halo and
+    dot-product reductions over NVLink"; BASELINE config 5 at a size whose set-up fits the bench budget): ONE T6
+    plane-stress SIMP_COMP problem on all N GPUs (femol_b200.dist.DistributedSIMP_COMP: strips of lattice rows,
+    distributed multigrid PCG, halo exchanges / reductions through peer memory), K timed steps after W warm-up steps,
+    CUDA events, max over ranks; then the same steps on rank 0 alone (the single-GPU SIMP_COMP) for the speed-up and
+    the density parity.  Strong scaling: the problem is fixed, N grows."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from femol_b200 import dist as fd
+    n = args.part_n
+
+    def build():
+        mesh = F.mesh.rectangle_T6(float(n), float(n), n, n)
+        gp = F.FEM_Problem('displacement', 'plane', mesh)
+        gp.define_materials(F.materials.general_isotropic())
+        gp.define_tensors(1)
+        gp.add_fixed_domain(F.domains.inside_box([0], [[0, float(n)]]), ddls=[0, 1])
+        gp.add_forces([0, -1.0], F.domains.inside_box([float(n)], [[n / 2.0 - 1, n / 2.0 + 1]]))
+        gp.solver_rtol = args.rtol
+        return gp
+
+    def timed(iterate, info):
+        for _ in range(args.warmup):
+            iterate()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        its = []
+        e0.record()
+        for _ in range(args.steps):
+            iterate()
+            its.append(info()['iterations'])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3, its
+
+    t0 = time.perf_counter()
+    gp = build()
+    comm = fd.create_comm(F)
+    opt = fd.DistributedSIMP_COMP(F, gp, comm, volfrac=0.4, penal=3, rmin=1.5)
+    setup_s = time.perf_counter() - t0
+    launches0 = int(F._lib.load().femol_launch_count(0))
+    dt, its = timed(opt.iterate, lambda: opt.solver_info)
+    launches = int(F._lib.load().femol_launch_count(0)) - launches0
+    t = torch.tensor([dt], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t[0])
+    stats = (F._lib.c_i64 * 3)()
+    healthy = F._lib.load().femol_dist_p2p_status(comm, stats) == 0
+    X = opt.density()
+    out = {'workload': 'T6 plane-stress cantilever SIMP_COMP, %dx%d elements (%.2fM DOF), ONE problem on %d GPUs'
+                       % (n, n, gp.mesh.N_nodes * 2 / 1e6, world),
+           'scaling': 'strong', 'value': args.steps / dt, 'unit': UNIT, 'ms_per_step': dt / args.steps * 1e3,
+           'pcg_iterations_per_step': its, 'distributed_levels': opt.part.n_dist, 'row_cuts': opt.part.cuts,
+           'transport': opt.transport, 'peer_memory_healthy': healthy,
+           'p2p_kernels': {'halo': int(stats[0]), 'allreduce': int(stats[1]), 'gather': int(stats[2])},
+           'gpu_launches_this_rank': launches, 'setup_s': setup_s}
+    transport = opt.transport
+    del opt
+    torch.cuda.synchronize()
+    dist.barrier()
+    F._lib.load().femol_dist_destroy(comm)
+    if rank == 0:
+        ref_p = build()
+        ref = F.SIMP_COMP(ref_p, volfrac=0.4, penal=3, rmin=1.5)
+        ref.archive = False
+    else:
+        ref_p = ref = None
+    if rank == 0:
+        for _ in range(args.warmup):
+            ref.iterate()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rits = []
+        e0.record()
+        for _ in range(args.steps):
+            ref.iterate()
+            rits.append(ref_p.solver_info['iterations'])
+        e1.record()
+        torch.cuda.synchronize()
+        rdt = e0.elapsed_time(e1) * 1e-3
+        out['single_gpu'] = {'value': args.steps / rdt, 'ms_per_step': rdt / args.steps * 1e3, 'pcg_iterations_per_step': rits}
+        out['speedup_vs_single_gpu'] = rdt / dt
+        out['density_max_abs_diff_vs_single_gpu'] = float(np.abs(X - ref.density()).max())
+        del ref, ref_p
+    dist.barrier()
+    return out if rank == 0 else None
 
 
 def time_kernel(torch, fn, reps):
@@ -410,6 +503,29 @@ def run_gpu(args):
                 'cpu_baseline': cpu, 'clocks': clocks,
                 'trajectory': {'change': [l[0] for l in log], 'compliance': [l[1] for l in log],
                                'pcg_relres': [l[2] for l in log]}}
+    if world > 1 and args.part_n > 0:
+        del opt, problem
+        torch.cuda.empty_cache()
+        # NCCL prints its version banner on stdout when the library's own communicator is created: keep stdout for
+        # the ONE JSON line (fd-level redirect to stderr for the duration of this leg)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            part = run_partitioned(F, args, rank, world)
+        except Exception as exc:      # the headline line must survive a failure of the secondary leg
+            part = {'error': '%s: %s' % (type(exc).__name__, exc)} if rank == 0 else None
+        finally:
+            sys.stdout.flush()
+            try:
+                import ctypes
+                ctypes.CDLL(None).fflush(None)     # the banner sits in the C stdio buffer of the process
+            except Exception:
+                pass
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
+        if line is not None:
+            line['partitioned'] = part
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -438,6 +438,7 @@ __device__ __forceinline__ void cta_copy_d2(double* __restrict__ dst, const doub
 __global__ void __launch_bounds__(1024)
 p2p_halo_kernel(double* x, int64_t rowd, int64_t own_lo, int64_t own_hi, int h_up, int h_down, int lower, int upper, int me,
                 P2PPeers peers, size_t hmax, unsigned long long* ctr) {
+    FEMOL_PDL_SYNC();
     const unsigned long long ep = ld_volatile_u64(&ctr[P2P_C_HALO_EP]) + 1ULL;
     const size_t par = (size_t)(ep & 1ULL);
     if (lower >= 0)   // my bottom owned rows -> the lower neighbour's "from upper" slot
@@ -460,6 +461,7 @@ p2p_halo_kernel(double* x, int64_t rowd, int64_t own_lo, int64_t own_hi, int h_u
 // W contributions in rank order (bit-identical result on all ranks).  One CTA.
 __global__ void __launch_bounds__(256)
 p2p_allreduce_kernel(double* buf, int count, int W, int me, P2PPeers peers, unsigned long long* ctr) {
+    FEMOL_PDL_SYNC();
     const unsigned long long ep = ld_volatile_u64(&ctr[P2P_C_RED_EP]) + 1ULL;
     const size_t par = (size_t)(ep & 1ULL);
     const int t = threadIdx.x;
@@ -488,6 +490,7 @@ p2p_allreduce_kernel(double* buf, int count, int W, int me, P2PPeers peers, unsi
 __global__ void __launch_bounds__(256)
 p2p_gather_kernel(const double* __restrict__ src, int64_t count, int64_t goff, int64_t total, double* __restrict__ out, int W, int me,
                   P2PPeers peers, size_t off_gather, size_t gmax, unsigned long long* ctr) {
+    FEMOL_PDL_SYNC();
     __shared__ unsigned long long s_ep;
     if (threadIdx.x == 0) s_ep = ld_volatile_u64(&ctr[P2P_C_GAT_EP]) + 1ULL;
     __syncthreads();
@@ -526,9 +529,10 @@ int femol_dist_exchange(femol_comm* c, double* x, int width, const femol_strip& 
     const bool lower = c->rank > 0, upper = c->rank < c->nranks - 1;
     const int64_t hmaxrows = s.h_up > s.h_down ? s.h_up : s.h_down;
     if (c->p2p.on && (size_t)(hmaxrows * rowd) <= c->p2p.halo_doubles && (rowd & 1) == 0 && ((uintptr_t)x & 15) == 0) {
-        p2p_halo_kernel<<<1, 1024, 0, st>>>(x, rowd, s.own_lo, s.own_hi, s.h_up, s.h_down, lower ? c->rank - 1 : -1,
-                                            upper ? c->rank + 1 : -1, c->rank, c->p2p.peers, c->p2p.halo_doubles, c->p2p.ctr);
-        FEMOL_LAUNCH_CHECK();
+        FEMOL_CUDA_CHECK(femol_launch_pdl(p2p_halo_kernel, dim3(1), dim3(1024), 0, st, x, rowd, s.own_lo, s.own_hi, s.h_up, s.h_down,
+                                          lower ? c->rank - 1 : -1, upper ? c->rank + 1 : -1, c->rank, c->p2p.peers,
+                                          c->p2p.halo_doubles, c->p2p.ctr));
+        femol_count_launch();
         ++c->p2p.n_halo;
         return FEMOL_OK;
     }
@@ -548,8 +552,9 @@ int femol_dist_exchange(femol_comm* c, double* x, int width, const femol_strip& 
 int femol_dist_allreduce(femol_comm* c, double* buf, int64_t count, cudaStream_t st) {
     if (c->nranks == 1 || count == 0) return FEMOL_OK;
     if (c->p2p.on && count <= P2P_RED_MAX && c->nranks * count <= 256) {
-        p2p_allreduce_kernel<<<1, 256, 0, st>>>(buf, (int)count, c->nranks, c->rank, c->p2p.peers, c->p2p.ctr);
-        FEMOL_LAUNCH_CHECK();
+        FEMOL_CUDA_CHECK(femol_launch_pdl(p2p_allreduce_kernel, dim3(1), dim3(256), 0, st, buf, (int)count, c->nranks, c->rank,
+                                          c->p2p.peers, c->p2p.ctr));
+        femol_count_launch();
         ++c->p2p.n_red;
         return FEMOL_OK;
     }
@@ -564,9 +569,9 @@ int femol_dist_allgather(femol_comm* c, const double* src, int64_t count, int64_
         int64_t blocks = (total / 2 + 255) / 256;
         if (blocks > 32) blocks = 32;
         if (blocks < 1) blocks = 1;
-        p2p_gather_kernel<<<(int)blocks, 256, 0, st>>>(src, count, goff, total, out, c->nranks, c->rank, c->p2p.peers, c->p2p.off_gather,
-                                                       c->p2p.gather_doubles, c->p2p.ctr);
-        FEMOL_LAUNCH_CHECK();
+        FEMOL_CUDA_CHECK(femol_launch_pdl(p2p_gather_kernel, dim3((unsigned)blocks), dim3(256), 0, st, src, count, goff, total, out,
+                                          c->nranks, c->rank, c->p2p.peers, c->p2p.off_gather, c->p2p.gather_doubles, c->p2p.ctr));
+        femol_count_launch();
         ++c->p2p.n_gather;
         return FEMOL_OK;
     }
@@ -675,6 +680,7 @@ template <int ND>
 __global__ void __launch_bounds__(DT)
 dg_update(int64_t n_nodes, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ u, double* __restrict__ r,
           double* __restrict__ sc, double* __restrict__ red, const double* __restrict__ dinv, double omega, double* __restrict__ z) {
+    FEMOL_PDL_SYNC();
     __shared__ double s_red[32];
     const bool done = sc[G_DONE] != 0.0;
     const double alpha = done ? 0.0 : sc[G_RZN] / sc[G_PQ];
@@ -706,6 +712,7 @@ dg_update(int64_t n_nodes, const double* __restrict__ p, const double* __restric
 
 // after the all-reduce of (r.z, r.r): rotate the r.z slots, count the iteration, test convergence
 __global__ void dg_iter_finalize(double* sc, int first) {
+    FEMOL_PDL_SYNC();
     if (sc[G_DONE] != 0.0) return;
     sc[G_RZO] = sc[G_RZN];
     sc[G_RZN] = sc[G_L0];
@@ -720,6 +727,7 @@ __global__ void dg_iter_finalize(double* sc, int first) {
 // first: p = z ; else p = z + (rz_new / rz_old) p     (owned range)
 __global__ void __launch_bounds__(DT)
 dg_direction(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ sc, int first) {
+    FEMOL_PDL_SYNC();
     if (sc[G_DONE] != 0.0) return;
     const double beta = first ? 0.0 : sc[G_RZN] / sc[G_RZO];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -774,29 +782,30 @@ int pcg_gmg_dist_run(femol_plan_t plan, femol_gmg* gmg, const double* vals, cons
         return FEMOL_OK;
     };
     auto rz_and_direction = [&](int first) -> int {
-        dg_dot<<<vgrid, DT, 0, st>>>(n_own, r + off, z + off, sc + G_L0, red);
-        FEMOL_LAUNCH_CHECK();
+        FEMOL_CUDA_CHECK(femol_launch_pdl(dg_dot, dim3(vgrid), dim3(DT), 0, st, n_own, (const double*)(r + off), (const double*)(z + off), sc + G_L0, red));
+        femol_count_launch();
         if ((rc = femol_dist_allreduce(c, sc + G_L0, 2, st)) != FEMOL_OK) return rc;
-        dg_iter_finalize<<<1, 1, 0, st>>>(sc, first);
-        dg_direction<<<vgrid, DT, 0, st>>>(n_own, z + off, p + off, sc, first);
-        FEMOL_LAUNCH_CHECK();
+        FEMOL_CUDA_CHECK(femol_launch_pdl(dg_iter_finalize, dim3(1), dim3(1), 0, st, sc, first));
+        femol_count_launch();
+        FEMOL_CUDA_CHECK(femol_launch_pdl(dg_direction, dim3(vgrid), dim3(DT), 0, st, n_own, (const double*)(z + off), p + off, (const double*)sc, first));
+        femol_count_launch();
         return FEMOL_OK;
     };
     auto iteration = [&]() -> int {
         if ((rc = femol_dist_exchange(c, p, nd, s, st)) != FEMOL_OK) return rc;
         if ((rc = femol_apply_launch(plan, vals, p, q, nullptr, nullptr, nullptr, st)) != FEMOL_OK) return rc;
-        dg_dot<<<vgrid, DT, 0, st>>>(n_own, p + off, q + off, sc + G_PQ, red);
-        FEMOL_LAUNCH_CHECK();
+        FEMOL_CUDA_CHECK(femol_launch_pdl(dg_dot, dim3(vgrid), dim3(DT), 0, st, n_own, (const double*)(p + off), (const double*)(q + off), sc + G_PQ, red));
+        femol_count_launch();
         if ((rc = femol_dist_allreduce(c, sc + G_PQ, 1, st)) != FEMOL_OK) return rc;
         const double* dv = first_sweep ? dinv0 + s.own_lo * s.row_nodes * nd * nd : nullptr;
-        if (nd == 2) dg_update<2><<<ngrid, DT, 0, st>>>(n_own_nodes, p + off, q + off, u + off, r + off, sc, red, dv, omega0, z + off);
-        else dg_update<6><<<ngrid, DT, 0, st>>>(n_own_nodes, p + off, q + off, u + off, r + off, sc, red, dv, omega0, z + off);
-        FEMOL_LAUNCH_CHECK();
+        if (nd == 2) FEMOL_CUDA_CHECK(femol_launch_pdl(dg_update<2>, dim3(ngrid), dim3(DT), 0, st, n_own_nodes, (const double*)(p + off), (const double*)(q + off), u + off, r + off, sc, red, dv, omega0, z + off));
+        else FEMOL_CUDA_CHECK(femol_launch_pdl(dg_update<6>, dim3(ngrid), dim3(DT), 0, st, n_own_nodes, (const double*)(p + off), (const double*)(q + off), u + off, r + off, sc, red, dv, omega0, z + off));
+        femol_count_launch();
         if ((rc = femol_gmg_dist_vcycle(gmg, r, z, st, first_sweep)) != FEMOL_OK) return rc;
         return rz_and_direction(0);
     };
     bool use_graph = getenv("FEMOL_NO_GRAPH") == nullptr && femol_comm_size(c) > 0;
-    long long graph_kernels = 0;
+    long long graph_kernels = 0, graph_p2p[3] = {0, 0, 0};
     for (int restart = 0; restart < 6; ++restart) {
         if ((rc = true_residual(restart)) != FEMOL_OK) return rc;
         if (h_sc[G_FF] == 0.0) {  // zero right-hand side (global norm): the solution is zero whatever the warm start was
@@ -813,10 +822,15 @@ int pcg_gmg_dist_run(femol_plan_t plan, femol_gmg* gmg, const double* vals, cons
         if (use_graph && !exec) {   // one CG iteration (static launch sequence: device-side scalars and epochs) -> CUDA graph
             cudaGraph_t graph = nullptr;
             const long long before = femol_launch_count(0);
+            const long long p2p_before[3] = {c->p2p.n_halo, c->p2p.n_red, c->p2p.n_gather};
             if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
                 const int crc = iteration();
                 graph_kernels = femol_launch_count(0) - before;
                 femol_count_launches(-graph_kernels);
+                // transfers captured, not executed: they are counted per graph launch below
+                graph_p2p[0] = c->p2p.n_halo - p2p_before[0]; graph_p2p[1] = c->p2p.n_red - p2p_before[1];
+                graph_p2p[2] = c->p2p.n_gather - p2p_before[2];
+                c->p2p.n_halo = p2p_before[0]; c->p2p.n_red = p2p_before[1]; c->p2p.n_gather = p2p_before[2];
                 const cudaError_t e = cudaStreamEndCapture(st, &graph);
                 if (crc != FEMOL_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
                 if (graph) cudaGraphDestroy(graph);
@@ -831,7 +845,11 @@ int pcg_gmg_dist_run(femol_plan_t plan, femol_gmg* gmg, const double* vals, cons
             first_batch = 0;
             if (nb > max_iter - total_iters) nb = max_iter - total_iters;
             for (int it = 0; it < nb; ++it) {      // every rank enqueues the same sequence, converged or not
-                if (exec) { FEMOL_CUDA_CHECK(cudaGraphLaunch(exec, st)); femol_count_launches(graph_kernels); }
+                if (exec) {
+                    FEMOL_CUDA_CHECK(cudaGraphLaunch(exec, st));
+                    femol_count_launches(graph_kernels);
+                    c->p2p.n_halo += graph_p2p[0]; c->p2p.n_red += graph_p2p[1]; c->p2p.n_gather += graph_p2p[2];
+                }
                 else if ((rc = iteration()) != FEMOL_OK) return rc;
             }
             FEMOL_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
