@@ -37,6 +37,8 @@ SIGNATURES = {
     'femol_assemble': (c_int, [P, P, c_int, P, c_int, P, c_dbl, P, P, P, P]),
     'femol_spmv': (c_int, [P, P, P, P, P]),
     'femol_spmv_csr': (c_int, [c_i64, P, P, P, P, P, P]),
+    'femol_to_f32': (c_int, [P, P, P, P]),
+    'femol_apply_f32': (c_int, [P, P, P, P, c_int, P, P, c_dbl, P]),
     'femol_plan_set_grid': (c_int, [P, c_i64, c_i64]),
     'femol_plan_set_matrix_free': (c_int, [P, c_i64, c_i64, P, P, P, P, P]),
     'femol_stress_q4': (c_int, [P, P, P, P, P, P, P, P]),

@@ -201,6 +201,22 @@ int femol_spmv_f32_epilogue_launch(femol_plan_t p, const float* vals32, const do
     return FEMOL_E_ARG;
 }
 
+// Single-precision copy of an assembled operator and the product from it (what the multigrid levels use): exposed for the
+// parity tests and the bench.  vals32: nnz floats (ndof = 2: node-blocked float4 layout).  mode: FEMOL_EPI_* (0 y = K x,
+// 1 y = rhs - K x, 2 y = x + omega Dinv (rhs - K x)).
+extern "C" int femol_to_f32(femol_plan_t p, const double* vals, float* vals32, void* stream) {
+    FEMOL_REQUIRE(p && vals && vals32, "femol_to_f32: null argument");
+    return femol_to_f32_launch(p, vals, vals32, (cudaStream_t)stream);
+}
+
+extern "C" int femol_apply_f32(femol_plan_t p, const float* vals32, const double* x, double* y, int mode, const double* rhs,
+                               const double* dinv, double omega, void* stream) {
+    FEMOL_REQUIRE(p && vals32 && x && y && x != y, "femol_apply_f32: null or aliased argument");
+    FEMOL_REQUIRE(mode >= 0 && mode <= 2 && (mode == 0 || rhs) && (mode != 2 || dinv), "femol_apply_f32: bad mode / missing operand");
+    const femol_epilogue ep = {mode, rhs, dinv, omega, nullptr, nullptr};
+    return femol_spmv_f32_epilogue_launch(p, vals32, x, y, ep, (cudaStream_t)stream);
+}
+
 extern "C" int femol_spmv(femol_plan_t p, const double* vals, const double* x, double* y, void* stream) {
     FEMOL_REQUIRE(p && vals && x && y, "femol_spmv: null argument");
     return femol_spmv_launch(p, vals, x, y, nullptr, nullptr, nullptr, (cudaStream_t)stream);

@@ -109,6 +109,12 @@ int femol_assemble(femol_plan_t plan, const double* e_base, int base_per_elem, c
 /* ---- K4: SpMV ------------------------------------------------------------------------------- */
 /* y = A x with A's values in plan CSR order, using the node-block adjacency for column indices */
 int femol_spmv(femol_plan_t plan, const double* vals, const double* x, double* y, void* stream);
+/* Single-precision copy of an assembled operator (vals32: nnz floats; ndof = 2: one float4 per node pair in adjacency
+ * order) and the product from it, as the multigrid levels use it (vectors and sums stay FP64): mode 0 y = K x,
+ * 1 y = rhs - K x, 2 y = x + omega Dinv (rhs - K x) (ndof = 2).  Exposed for the parity tests and the bench. */
+int femol_to_f32(femol_plan_t plan, const double* vals, float* vals32, void* stream);
+int femol_apply_f32(femol_plan_t plan, const float* vals32, const double* x, double* y, int mode, const double* rhs,
+                    const double* dinv, double omega, void* stream);
 /* generic CSR (any matrix, e.g. a scipy one) */
 int femol_spmv_csr(int64_t n_rows, const int32_t* indptr, const int32_t* indices, const double* vals,
                    const double* x, double* y, void* stream);

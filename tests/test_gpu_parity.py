@@ -1160,3 +1160,36 @@ def test_hourglass_hierarchy_on_plates_with_free_edges(F):
     ps.add_fixed_domain(F.domains.inside_box([[0, 24.]], [0, 12.]), ddls=[2]); ps.add_fixed_domain(F.domains.inside_box([0, 24.], [[0, 12.]]), ddls=[2])
     ps.assemble('K'); ps._gmg_ready()
     assert ps._gmg2 is None
+
+
+@pytest.mark.parametrize('kind,nx,ny', [('Q4', 40, 21), ('Q4', 63, 1), ('Q4', 130, 70), ('T6', 24, 12), ('T6', 31, 17), ('T3', 33, 15)])
+def test_single_precision_products(F, kind, nx, ny):
+    """femol_to_f32 / femol_apply_f32 (the operator copies the multigrid levels multiply with; rows of 4 - 19 node blocks)
+    against the FP64 matrix rounded to single precision: y = K x, y = rhs - K x, y = x + omega Dinv (rhs - K x)."""
+    import torch
+    if kind == 'Q4':
+        p, x = _gmg_problem(F, nx, ny, 'plane')
+        p.assemble('K', X={'quad': x}, p=3)
+    else:
+        p, x = _lattice_problem(F, kind, nx, ny)
+        p.assemble('K', X={'triangle': x}, p=3)
+    d = p.device
+    L = F._lib
+    K = p.K
+    K32 = K.copy(); K32.data = K32.data.astype(np.float32).astype(np.float64)
+    v32 = torch.empty(d.nnz, dtype=torch.float32, device='cuda')
+    L.call('femol_to_f32', d.plan, p.K_values.data_ptr(), v32.data_ptr(), L.stream())
+    rng = np.random.default_rng(11)
+    xs, rhs = rng.standard_normal(d.n), rng.standard_normal(d.n)
+    xd, rd = torch.from_numpy(xs).cuda(), torch.from_numpy(rhs).cuda()
+    dinv = torch.empty(d.n_nodes * 4, dtype=torch.float64, device='cuda')
+    L.call('femol_precond_setup', d.plan, p.K_values.data_ptr(), 2, dinv.data_ptr(), L.stream())
+    D = dinv.cpu().numpy().reshape(d.n_nodes, 2, 2)
+    Kx = K32 @ xs
+    refs = [Kx, rhs - Kx, xs + 0.7 * np.einsum('nab,nb->na', D, (rhs - Kx).reshape(-1, 2)).reshape(-1)]
+    for mode in range(3):
+        y = torch.full_like(xd, float('nan'))
+        L.call('femol_apply_f32', d.plan, v32.data_ptr(), xd.data_ptr(), y.data_ptr(), mode, rd.data_ptr(), dinv.data_ptr(), 0.7, L.stream())
+        assert rel(y.cpu().numpy(), refs[mode]) < 1e-13, mode
+    with pytest.raises(L.FemolError):
+        L.call('femol_apply_f32', d.plan, v32.data_ptr(), xd.data_ptr(), xd.data_ptr(), 0, None, None, 0.0, L.stream())
