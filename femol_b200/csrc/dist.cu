@@ -71,21 +71,20 @@ int load_nccl() {
 }  // namespace
 
 // Peer-memory transport (femol_dist_p2p_open / _attach): every rank owns one cudaMalloc'ed WINDOW that all other ranks
-// of the box map through CUDA IPC (NVLink / NVSwitch peer stores).  Layout of a window:
-//   [P2P_OFF_FLAGS]   u64 halo_flag[2] (last epoch pushed by the lower / upper neighbour), red_flag[16], gat_flag[16]
-//   [P2P_OFF_RED]     double red[2 parities][16 ranks][16]      partial sums of the scalar all-reduce
-//   [P2P_OFF_HALO]    double halo[2 (from lower, from upper)][2 parities][halo_doubles]
-//   [off_gather]      double gather[2 parities][gather_doubles]
-// A transfer = the sender's kernel stores the payload into the receiver's window (slot = epoch parity), fences at system
-// scope and releases the receiver's flag with its epoch; the receiver's kernel spins on its own flag (acquire) and
-// copies the slot out.  Epochs are DEVICE counters advanced by the kernels themselves, so the launch sequence is static
-// (CUDA-graph capturable).  Two parities suffice: a rank can only push epoch k + 2 after it completed transfer k + 1,
-// which needed the receiver's push k + 1, which the receiver's stream issues after its transfer-k kernel has finished.
+// of the box map through CUDA IPC (NVLink / NVSwitch peer stores).  A window is an array of 16-byte elements, each one
+// double with its own arrival flags (LLElem below):
+//   [P2P_OFF_RED]     red[2 parities][16 ranks][16]                       partial sums of the scalar all-reduce
+//   [P2P_OFF_HALO]    halo[2 (from lower, from upper)][2 parities][halo_doubles]
+//   [off_gather]      gather[2 parities][gather_doubles]
+// A transfer = the sender's kernel stores payload + epoch into the receiver's window (slot = epoch parity) with 16-byte
+// stores; the receiver's kernel polls its own window until every element carries that epoch.  Epochs are DEVICE counters
+// advanced by the kernels themselves, so the launch sequence is static (CUDA-graph capturable).  Two parities suffice: a
+// rank can only push epoch k + 2 after it completed transfer k + 1, which needed the receiver's push k + 1, which the
+// receiver's stream issues after its transfer-k kernel has finished reading slot k.
 constexpr int P2P_MAX_RANKS = 16;
 constexpr int P2P_RED_MAX = 16;
-constexpr size_t P2P_OFF_FLAGS = 0, P2P_OFF_RED = 1024, P2P_OFF_HALO = 8192;
-enum { P2P_C_HALO_EP = 0, P2P_C_HALO_ARRIVE = 1, P2P_C_HALO_DONE = 2, P2P_C_RED_EP = 3, P2P_C_GAT_EP = 4, P2P_C_GAT_ARRIVE = 5,
-       P2P_C_GAT_DONE = 6, P2P_C_ERR = 7, P2P_C_N = 8 };
+constexpr size_t P2P_OFF_RED = 0, P2P_OFF_HALO = 2 * P2P_MAX_RANKS * P2P_RED_MAX * 16;
+enum { P2P_C_HALO_EP = 0, P2P_C_RED_EP = 3, P2P_C_GAT_EP = 4, P2P_C_GAT_DONE = 6, P2P_C_ERR = 7, P2P_C_N = 8 };
 
 struct P2PPeers { char* w[P2P_MAX_RANKS]; };
 
@@ -393,68 +392,76 @@ int femol_comm_size(const femol_comm* c) { return c->nranks; }
 
 namespace {
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// spin until *flag >= ep; gives up after ~2 s (a peer died): raises the error counter, every later wait returns at once
-__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long ep, unsigned long long* ctr) {
-    if (ld_volatile_u64(&ctr[P2P_C_ERR]) != 0ULL) return;
-    const long long t0 = clock64();
-    while (ld_acquire_sys(flag) < ep) {
-        if (clock64() - t0 > 4000000000LL) { atomicExch(&ctr[P2P_C_ERR], 1ULL); return; }
+
+// One window element = one double with its own arrival flags: {low word, epoch, high word, epoch} written by ONE 16-byte
+// store (each 8-byte half validates itself, so the element is safe even where only 8-byte stores are atomic).  The
+// receiver polls the element until both flags equal the epoch it expects - no fence, no separate flag, no second
+// NVLink traversal: a transfer costs one store latency.  (NCCL's LL protocol, for FP64 payloads.)
+struct __align__(16) LLElem { unsigned lo, f0, hi, f1; };
+
+__device__ __forceinline__ void ll_store(LLElem* p, double v, unsigned ep) {
+    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(ep), "r"(hi), "r"(ep) : "memory");
+}
+// spin until the element carries epoch `ep`; gives up after ~2 s (a peer died): raises the error counter, after which no
+// wait blocks any more (results are garbage, the host reports the error)
+__device__ __forceinline__ double ll_wait(const LLElem* p, unsigned ep, unsigned long long* ctr) {
+    unsigned lo, f0, hi, f1;
+    long long t0 = 0;
+    unsigned spins = 0;
+    while (true) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(p) : "memory");
+        if (f0 == ep && f1 == ep) break;
+        if ((++spins & 1023u) == 0u) {
+            if (ld_volatile_u64(&ctr[P2P_C_ERR]) != 0ULL) break;
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 4000000000LL) { atomicExch(&ctr[P2P_C_ERR], 1ULL); break; }
+        }
     }
+    return __hiloint2double((int)hi, (int)lo);
 }
-__device__ __forceinline__ unsigned long long* win_flags(char* w) { return reinterpret_cast<unsigned long long*>(w + P2P_OFF_FLAGS); }
+__device__ __forceinline__ unsigned epoch32(unsigned long long ep) { return (unsigned)(ep % 0xFFFFFFFFULL) + 1u; }   // never 0 (the memset value)
 
-__device__ __forceinline__ void copy_d2(double* __restrict__ dst, const double* __restrict__ src, int64_t n, bool from_window) {
-    // n is even and both pointers are 16-byte aligned (rows of an even number of doubles)
-    const int64_t n2 = n >> 1;
-    const double2* s2 = reinterpret_cast<const double2*>(src);
-    double2* d2 = reinterpret_cast<double2*>(dst);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
-        d2[i] = from_window ? __ldcg(&s2[i]) : s2[i];
-}
+__device__ __forceinline__ LLElem* win_halo(char* w) { return reinterpret_cast<LLElem*>(w + P2P_OFF_HALO); }
+__device__ __forceinline__ LLElem* win_red(char* w) { return reinterpret_cast<LLElem*>(w + P2P_OFF_RED); }
 
-// Halo exchange of one vector in ONE CTA (messages are a few lattice rows: 30 - 270 KB): push my boundary rows into the
-// neighbours' windows, fence, release their flags, acquire mine, copy the rows out.  No grid-level tickets: every
-// microsecond of this kernel is on the critical path of the V-cycle (13 exchanges per CG iteration).
-__device__ __forceinline__ void cta_copy_d2(double* __restrict__ dst, const double* __restrict__ src, int64_t n, bool from_window) {
-    const int64_t n2 = n >> 1;
-    const double2* s2 = reinterpret_cast<const double2*>(src);
-    double2* d2 = reinterpret_cast<double2*>(dst);
-    for (int64_t i = threadIdx.x; i < n2; i += blockDim.x) d2[i] = from_window ? __ldcg(&s2[i]) : s2[i];
-}
-
+// Halo exchange of one vector in ONE CTA (messages are a few lattice rows: 4 - 11 k doubles): store my boundary rows
+// into the neighbours' mailboxes over NVLink, then poll my own mailbox element by element into the ghost rows.  Every
+// microsecond of this kernel is on the critical path of the V-cycle (1 + 3 n_dist exchanges per CG iteration).
 __global__ void __launch_bounds__(1024)
 p2p_halo_kernel(double* x, int64_t rowd, int64_t own_lo, int64_t own_hi, int h_up, int h_down, int lower, int upper, int me,
                 P2PPeers peers, size_t hmax, unsigned long long* ctr) {
     FEMOL_PDL_SYNC();
-    const unsigned long long ep = ld_volatile_u64(&ctr[P2P_C_HALO_EP]) + 1ULL;
-    const size_t par = (size_t)(ep & 1ULL);
-    if (lower >= 0)   // my bottom owned rows -> the lower neighbour's "from upper" slot
-        cta_copy_d2(reinterpret_cast<double*>(peers.w[lower] + P2P_OFF_HALO) + (2 + par) * hmax, x + own_lo * rowd, h_down * rowd, false);
-    if (upper >= 0)   // my top owned rows -> the upper neighbour's "from lower" slot
-        cta_copy_d2(reinterpret_cast<double*>(peers.w[upper] + P2P_OFF_HALO) + (0 + par) * hmax, x + (own_hi - h_up) * rowd, h_up * rowd, false);
-    __threadfence_system();
-    __syncthreads();           // every thread has read the epoch and its stores are performed system-wide
-    unsigned long long* mine = win_flags(peers.w[me]);
-    if (threadIdx.x == 0 && lower >= 0) { st_release_sys(&win_flags(peers.w[lower])[1], ep); wait_flag(&mine[0], ep, ctr); }
-    if (threadIdx.x == 32 && upper >= 0) { st_release_sys(&win_flags(peers.w[upper])[0], ep); wait_flag(&mine[1], ep, ctr); }
-    __syncthreads();
-    const double* box = reinterpret_cast<const double*>(peers.w[me] + P2P_OFF_HALO);
-    if (lower >= 0) cta_copy_d2(x + (own_lo - h_up) * rowd, box + (0 + par) * hmax, h_up * rowd, true);
-    if (upper >= 0) cta_copy_d2(x + own_hi * rowd, box + (2 + par) * hmax, h_down * rowd, true);
-    if (threadIdx.x == 0) ctr[P2P_C_HALO_EP] = ep;
+    const unsigned long long ep64 = ld_volatile_u64(&ctr[P2P_C_HALO_EP]) + 1ULL;
+    const unsigned ep = epoch32(ep64);
+    const size_t par = (size_t)(ep64 & 1ULL);
+    const int n_dn = (int)(h_down * rowd), n_up = (int)(h_up * rowd);
+    if (lower >= 0) {   // my bottom owned rows -> the lower neighbour's "from upper" slot
+        LLElem* dst = win_halo(peers.w[lower]) + (2 + par) * hmax;
+        const double* src = x + own_lo * rowd;
+        for (int i = threadIdx.x; i < n_dn; i += blockDim.x) ll_store(dst + i, src[i], ep);
+    }
+    if (upper >= 0) {   // my top owned rows -> the upper neighbour's "from lower" slot
+        LLElem* dst = win_halo(peers.w[upper]) + (0 + par) * hmax;
+        const double* src = x + (own_hi - h_up) * rowd;
+        for (int i = threadIdx.x; i < n_up; i += blockDim.x) ll_store(dst + i, src[i], ep);
+    }
+    const LLElem* box = win_halo(peers.w[me]);
+    if (lower >= 0) {
+        double* dst = x + (own_lo - h_up) * rowd;
+        for (int i = threadIdx.x; i < n_up; i += blockDim.x) dst[i] = ll_wait(box + (0 + par) * hmax + i, ep, ctr);
+    }
+    if (upper >= 0) {
+        double* dst = x + own_hi * rowd;
+        for (int i = threadIdx.x; i < n_dn; i += blockDim.x) dst[i] = ll_wait(box + (2 + par) * hmax + i, ep, ctr);
+    }
+    __syncthreads();           // every thread has read the epoch counter
+    if (threadIdx.x == 0) ctr[P2P_C_HALO_EP] = ep64;
 }
 
 // In-place sum of `count` (<= 16) doubles over all ranks: every rank stores its values into every window, then adds the
@@ -462,62 +469,47 @@ p2p_halo_kernel(double* x, int64_t rowd, int64_t own_lo, int64_t own_hi, int h_u
 __global__ void __launch_bounds__(256)
 p2p_allreduce_kernel(double* buf, int count, int W, int me, P2PPeers peers, unsigned long long* ctr) {
     FEMOL_PDL_SYNC();
-    const unsigned long long ep = ld_volatile_u64(&ctr[P2P_C_RED_EP]) + 1ULL;
-    const size_t par = (size_t)(ep & 1ULL);
+    __shared__ double s_val[P2P_MAX_RANKS * P2P_RED_MAX];
+    const unsigned long long ep64 = ld_volatile_u64(&ctr[P2P_C_RED_EP]) + 1ULL;
+    const unsigned ep = epoch32(ep64);
+    const size_t par = (size_t)(ep64 & 1ULL);
     const int t = threadIdx.x;
     if (t < W * count) {
         const int peer = t / count, k = t - peer * count;
-        reinterpret_cast<double*>(peers.w[peer] + P2P_OFF_RED)[(par * P2P_MAX_RANKS + me) * P2P_RED_MAX + k] = buf[k];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (t < W) {
-        st_release_sys(&win_flags(peers.w[t])[2 + me], ep);
-        wait_flag(&win_flags(peers.w[me])[2 + t], ep, ctr);
+        ll_store(win_red(peers.w[peer]) + (par * P2P_MAX_RANKS + me) * P2P_RED_MAX + k, buf[k], ep);
+        s_val[t] = ll_wait(win_red(peers.w[me]) + (par * P2P_MAX_RANKS + peer) * P2P_RED_MAX + k, ep, ctr);   // rank `peer`'s k-th value
     }
     __syncthreads();
     if (t < count) {
-        const double* red = reinterpret_cast<const double*>(peers.w[me] + P2P_OFF_RED) + par * P2P_MAX_RANKS * P2P_RED_MAX;
         double sum = 0.0;
-        for (int r = 0; r < W; ++r) sum += __ldcg(&red[r * P2P_RED_MAX + t]);
+        for (int r = 0; r < W; ++r) sum += s_val[r * count + t];
         buf[t] = sum;
     }
-    if (t == 0) ctr[P2P_C_RED_EP] = ep;
+    if (t == 0) ctr[P2P_C_RED_EP] = ep64;
 }
 
-// All-gather by pushes: my `count` doubles go to offset `goff` of the gather slot of EVERY window; once all W pieces
-// have arrived the slot (total doubles) is copied to `out`.
+// All-gather by pushes: my `count` doubles go to offset `goff` of the gather slot of EVERY window; the whole slot (total
+// doubles) is polled into `out`.
 __global__ void __launch_bounds__(256)
 p2p_gather_kernel(const double* __restrict__ src, int64_t count, int64_t goff, int64_t total, double* __restrict__ out, int W, int me,
                   P2PPeers peers, size_t off_gather, size_t gmax, unsigned long long* ctr) {
     FEMOL_PDL_SYNC();
-    __shared__ unsigned long long s_ep;
-    if (threadIdx.x == 0) s_ep = ld_volatile_u64(&ctr[P2P_C_GAT_EP]) + 1ULL;
-    __syncthreads();
-    const unsigned long long ep = s_ep;
-    const size_t par = (size_t)(ep & 1ULL);
+    const unsigned long long ep64 = ld_volatile_u64(&ctr[P2P_C_GAT_EP]) + 1ULL;
+    const unsigned ep = epoch32(ep64);
+    const size_t par = (size_t)(ep64 & 1ULL);
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
     for (int r = 0; r < W; ++r) {
         const int peer = (me + r) % W;      // spread the ranks' first targets over the switch
-        copy_d2(reinterpret_cast<double*>(peers.w[peer] + off_gather) + par * gmax + goff, src, count, false);
+        LLElem* dst = reinterpret_cast<LLElem*>(peers.w[peer] + off_gather) + par * gmax + goff;
+        for (int64_t i = tid; i < count; i += nth) ll_store(dst + i, src[i], ep);
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned long long t = atomicAdd(&ctr[P2P_C_GAT_ARRIVE], 1ULL);
-        if (t == (unsigned long long)gridDim.x - 1ULL) {
-            ctr[P2P_C_GAT_ARRIVE] = 0ULL;
-            __threadfence();
-            for (int r = 0; r < W; ++r) st_release_sys(&win_flags(peers.w[r])[2 + P2P_MAX_RANKS + me], ep);
-        }
-    }
-    if (threadIdx.x < W) wait_flag(&win_flags(peers.w[me])[2 + P2P_MAX_RANKS + threadIdx.x], ep, ctr);
-    __syncthreads();
-    copy_d2(out, reinterpret_cast<const double*>(peers.w[me] + off_gather) + par * gmax, total, true);
+    const LLElem* box = reinterpret_cast<const LLElem*>(peers.w[me] + off_gather) + par * gmax;
+    for (int64_t i = tid; i < total; i += nth) out[i] = ll_wait(box + i, ep, ctr);
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned long long t = atomicAdd(&ctr[P2P_C_GAT_DONE], 1ULL);
-        if (t == (unsigned long long)gridDim.x - 1ULL) { ctr[P2P_C_GAT_DONE] = 0ULL; ctr[P2P_C_GAT_EP] = ep; }
+        if (t == (unsigned long long)gridDim.x - 1ULL) { ctr[P2P_C_GAT_DONE] = 0ULL; ctr[P2P_C_GAT_EP] = ep64; }
     }
 }
 
@@ -528,7 +520,7 @@ int femol_dist_exchange(femol_comm* c, double* x, int width, const femol_strip& 
     const int64_t rowd = s.row_nodes * width;
     const bool lower = c->rank > 0, upper = c->rank < c->nranks - 1;
     const int64_t hmaxrows = s.h_up > s.h_down ? s.h_up : s.h_down;
-    if (c->p2p.on && (size_t)(hmaxrows * rowd) <= c->p2p.halo_doubles && (rowd & 1) == 0 && ((uintptr_t)x & 15) == 0) {
+    if (c->p2p.on && (size_t)(hmaxrows * rowd) <= c->p2p.halo_doubles) {
         FEMOL_CUDA_CHECK(femol_launch_pdl(p2p_halo_kernel, dim3(1), dim3(1024), 0, st, x, rowd, s.own_lo, s.own_hi, s.h_up, s.h_down,
                                           lower ? c->rank - 1 : -1, upper ? c->rank + 1 : -1, c->rank, c->p2p.peers,
                                           c->p2p.halo_doubles, c->p2p.ctr));
@@ -565,8 +557,8 @@ int femol_dist_allreduce(femol_comm* c, double* buf, int64_t count, cudaStream_t
 // out[0..total) = concatenation over ranks of their pieces (src: count doubles, stored at offset goff); the pieces
 // tile [0, total).  P2P pushes when the transport is attached, else a zero-padded all-reduce.
 int femol_dist_allgather(femol_comm* c, const double* src, int64_t count, int64_t goff, int64_t total, double* out, cudaStream_t st) {
-    if (c->p2p.on && (size_t)total <= c->p2p.gather_doubles && ((count | goff | total) & 1) == 0) {
-        int64_t blocks = (total / 2 + 255) / 256;
+    if (c->p2p.on && (size_t)total <= c->p2p.gather_doubles) {
+        int64_t blocks = (total + 4 * 256 - 1) / (4 * 256);
         if (blocks > 32) blocks = 32;
         if (blocks < 1) blocks = 1;
         FEMOL_CUDA_CHECK(femol_launch_pdl(p2p_gather_kernel, dim3((unsigned)blocks), dim3(256), 0, st, src, count, goff, total, out,
@@ -591,8 +583,8 @@ extern "C" int femol_dist_p2p_open(femol_comm* c, int64_t halo_doubles, int64_t 
     femol_p2p& w = c->p2p;
     w.halo_doubles = (size_t)((halo_doubles + 31) & ~31LL);
     w.gather_doubles = (size_t)((gather_doubles + 31) & ~31LL);
-    w.off_gather = P2P_OFF_HALO + 4 * w.halo_doubles * sizeof(double);
-    w.win_bytes = w.off_gather + 2 * w.gather_doubles * sizeof(double);
+    w.off_gather = P2P_OFF_HALO + 4 * w.halo_doubles * 16;
+    w.win_bytes = w.off_gather + 2 * w.gather_doubles * 16;
     FEMOL_CUDA_CHECK(cudaMalloc(&w.win, w.win_bytes));
     FEMOL_CUDA_CHECK(cudaMemset(w.win, 0, w.win_bytes));
     FEMOL_CUDA_CHECK(cudaMalloc(&w.ctr, P2P_C_N * sizeof(unsigned long long)));

@@ -250,12 +250,14 @@ int femol_dist_allreduce_sum(femol_comm_t comm, double* buf, int64_t count, void
 /* Peer-memory transport (default; NCCL send/recv + all-reduce is the fallback and the baseline it is measured against):
  * every rank opens a WINDOW (cudaMalloc + CUDA IPC handle, 64 bytes) sized by femol_gmg_dist_p2p_sizes (h_out[0] doubles
  * of the largest halo message, h_out[1] doubles of the gathered level), the host all-gathers the handles
- * (torch.distributed) and every rank attaches them.  From then on a halo exchange is ONE kernel per rank that stores its
- * boundary rows straight into the neighbours' windows over NVLink, releases a flag (st.release.sys) and spins on its own
- * (ld.acquire.sys); the 1-2 scalar all-reduces of a CG iteration and the gather of the coarse residual work the same
- * way (all-to-all pushes, summed in rank order: bit-identical on all ranks).  Epochs are device counters, so the launch
- * sequence is static.  femol_dist_p2p_status: 0 healthy, 1 a wait timed out (~2 s: peer lost); h_stats[3] (optional)
- * = halo / all-reduce / gather kernels launched. */
+ * (torch.distributed) and every rank attaches them.  From then on a halo exchange is ONE single-CTA kernel per rank: it
+ * stores its boundary rows straight into the neighbours' windows over NVLink as 16-byte elements {low word, epoch, high
+ * word, epoch} and polls its own window until every element carries the epoch it expects - no fence, no separate flag,
+ * one store latency per transfer (NCCL's LL protocol for FP64 payloads).  The 1-2 scalar all-reduces of a CG iteration
+ * and the gather of the coarse residual work the same way (all-to-all pushes, summed in rank order: bit-identical on all
+ * ranks).  Epochs are device counters, so the launch sequence is static (CUDA-graph capturable).
+ * femol_dist_p2p_status: 0 healthy, 1 a wait timed out (~2 s: peer lost); h_stats[3] (optional) = halo / all-reduce /
+ * gather kernels launched. */
 int femol_gmg_dist_p2p_sizes(femol_gmg_t gmg, int64_t* h_out);
 int femol_dist_p2p_open(femol_comm_t comm, int64_t halo_doubles, int64_t gather_doubles, void* h_handle64);
 int femol_dist_p2p_attach(femol_comm_t comm, const void* h_handles);

@@ -74,10 +74,13 @@ def main():
     ap.add_argument('--rtol', type=float, default=1e-9)
     ap.add_argument('--no-reference', action='store_true', help='skip the single-GPU run (large meshes)')
     ap.add_argument('--out', default=None)
+    ap.add_argument('--latency', action='store_true', help='time back-to-back halo exchanges / scalar all-reduces (CUDA events)')
     ap.add_argument('--profile', type=int, default=0, help='profile this many extra iterations with CUPTI (rank 0 prints)')
     a = ap.parse_args()
     import femol_b200 as F
     from femol_b200 import dist as fd
+    if os.environ.get('FEMOL_AB_LIB'):          # A/B runs against another build of the library
+        F._lib.LIB_PATH = os.environ['FEMOL_AB_LIB']
     rank, world = fd.init_process_group()
     if world == 1:
         torch.cuda.set_device(0)
@@ -99,6 +102,29 @@ def main():
         log.append({'c': c, 'change': change, 'pcg': opt.solver_info['iterations'], 'relres': opt.solver_info['relres'],
                     'status': opt.solver_info['status']})
     X = opt.density()
+    lat = None
+    if a.latency:
+        L = F._lib
+        d = opt.local_problem.device
+        v = torch.zeros(d.n, dtype=torch.float64, device=d.dev)
+        sc = torch.zeros(16, dtype=torch.float64, device=d.dev)
+        lat = {}
+        for name, fn in (('halo_exchange_level0_us', lambda: L.call('femol_gmg_dist_exchange', opt._gmg, 0, L.ptr(v), gp.N_dof, L.stream())),
+                         ('halo_exchange_level%d_us' % (opt.part.n_dist - 1),
+                          lambda: L.call('femol_gmg_dist_exchange', opt._gmg, opt.part.n_dist - 1, L.ptr(v), gp.N_dof, L.stream())),
+                         ('allreduce_2_doubles_us', lambda: L.call('femol_dist_allreduce_sum', comm, L.ptr(sc), 2, L.stream()))):
+            for _ in range(20):
+                fn()
+            torch.cuda.synchronize()
+            if world > 1:
+                torch.distributed.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(500):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            lat[name] = e0.elapsed_time(e1) / 500 * 1e3
     if a.profile:
         kernel_profile(opt, a.profile, rank)
         for mode in (True, 'host'):
@@ -112,7 +138,7 @@ def main():
     res = {'mesh': a.mesh, 'model': a.model, 'nx': a.nx, 'ny': a.ny, 'world': world, 'n_dist': opt.part.n_dist, 'cuts': opt.part.cuts,
            'ndof': int(gp.mesh.N_nodes * gp.N_dof), 'setup_s': t_setup, 'iteration_s': times, 'log': log,
            'gpu_mem_gb': torch.cuda.max_memory_allocated() / 1e9, 'transport': getattr(opt, 'transport', None),
-           'launches': int(F._lib.load().femol_launch_count(0))}
+           'launches': int(F._lib.load().femol_launch_count(0)), 'latency': lat}
     ok = True
     if not a.no_reference and rank == 0:
         ref = build_problem(F, a.mesh, a.nx, a.ny, a.model)
