@@ -314,7 +314,8 @@ def run_gpu(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        import datetime
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local), timeout=datetime.timedelta(seconds=300))
     L = F._lib.require_gpu()
     t_setup = time.perf_counter()
     problem, opt = build_gpu_problem(F, args.nx, args.ny, args.rtol, args.precond)
@@ -526,11 +527,15 @@ def run_gpu(args):
             os.close(saved_fd)
         if line is not None:
             line['partitioned'] = part
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    if line is not None:
+    if line is not None:          # printed before the final collectives: a failed secondary leg must not cost the headline
         print(json.dumps(line))
+        sys.stdout.flush()
+    if world > 1:
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 def main():
