@@ -477,7 +477,7 @@ class DistributedSIMP_COMP(object):
         self._red_ws = torch.zeros(int(L.load().femol_reduce_workspace_doubles()), dtype=torch.float64, device=dev)
         gm.compute_element_centers()
         self._filter = TOM_SIMP.build_filter(gm, rmin, dev)
-        self._mask = None
+        self._mask, self._mask_key = None, (None, None)
         self._loc_elems = up(self.local_elements, np.int64)
         own_local = np.nonzero(own)[0]
         self._own_local = up(own_local, np.int64)
@@ -643,6 +643,10 @@ class DistributedSIMP_COMP(object):
         self._scal[0] = c_loc
         self._tick('gather')
         TOM_SIMP.apply_filter(self._filter, self._x, self._dc_pad, self._dcf)
+        key = (getattr(self, 'solid_domain', None), getattr(self, 'void_domain', None))     # TOM_SIMP.py:299-303, 315-331
+        if key != self._mask_key:
+            self._mask = TOM_SIMP.domain_mask(self.gp.mesh, key[0], key[1], d.dev)
+            self._mask_key = key
         L.call('femol_oc_update', self.n_elem, L.ptr(self._x), L.ptr(self._dcf), 0, float(self.f), None, L.ptr(self._mask),
                L.ptr(self._xn), self._scal.data_ptr() + 4 * 8, L.ptr(self._red_ws), L.stream())
         self._x, self._xn = self._xn, self._x

@@ -42,6 +42,12 @@ def cfg3(scale):
         t0 = sync(); p.assemble('K'); t1 = sync(); U = p.solve_device(); t2 = sync()
         out[pc] = {'assemble_s': t1 - t0, 'solve_s': t2 - t1, 'pcg': dict(p.solver_info),
                    'w_max': float(U[2::6].abs().max())}
+        # again with the plans / hierarchy in place (what every later solve of the same mesh costs): re-assembly,
+        # hierarchy refresh, solve from a zero start
+        p._U_dev = None
+        t0 = sync(); p.assemble('K'); t1 = sync(); U = p.solve_device(); t2 = sync()
+        out[pc]['second_assemble_s'] = t1 - t0
+        out[pc]['second_solve_s'] = t2 - t1
     out['nnz'] = p.device.nnz
     return out
 
