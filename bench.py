@@ -507,29 +507,14 @@ def run_gpu(args):
     if world > 1 and args.part_n > 0:
         del opt, problem
         torch.cuda.empty_cache()
-        # NCCL prints its version banner on stdout when the library's own communicator is created: keep stdout for
-        # the ONE JSON line (fd-level redirect to stderr for the duration of this leg)
-        sys.stdout.flush()
-        saved_fd = os.dup(1)
-        os.dup2(2, 1)
         try:
             part = run_partitioned(F, args, rank, world)
         except Exception as exc:      # the headline line must survive a failure of the secondary leg
             part = {'error': '%s: %s' % (type(exc).__name__, exc)} if rank == 0 else None
-        finally:
-            sys.stdout.flush()
-            try:
-                import ctypes
-                ctypes.CDLL(None).fflush(None)     # the banner sits in the C stdio buffer of the process
-            except Exception:
-                pass
-            os.dup2(saved_fd, 1)
-            os.close(saved_fd)
         if line is not None:
             line['partitioned'] = part
     if line is not None:          # printed before the final collectives: a failed secondary leg must not cost the headline
-        print(json.dumps(line))
-        sys.stdout.flush()
+        emit(line)
     if world > 1:
         try:
             dist.barrier()
@@ -538,11 +523,27 @@ def run_gpu(args):
             pass
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
     if args.impl == 'reference':
         run_reference(args)
     else:
+        # NCCL prints a version banner on stdout (C stdio) when a communicator is created: for the duration of the run
+        # file descriptor 1 points to stderr, and the JSON line goes to a duplicate of the original stdout
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
         run_gpu(args)
 
 

@@ -577,20 +577,31 @@ int femol_dist_allgather(femol_comm* c, const double* src, int64_t count, int64_
 // 3. every rank: femol_dist_p2p_attach(all handles); 4. a host barrier before the first transfer.
 extern "C" int femol_dist_p2p_open(femol_comm* c, int64_t halo_doubles, int64_t gather_doubles, void* h_handle64) {
     FEMOL_REQUIRE(c && h_handle64 && halo_doubles >= 0 && gather_doubles >= 0, "femol_dist_p2p_open: bad argument");
-    FEMOL_REQUIRE(!c->p2p.win, "femol_dist_p2p_open: window already open");
     FEMOL_REQUIRE(c->nranks <= P2P_MAX_RANKS, "femol_dist_p2p_open: too many ranks");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     femol_p2p& w = c->p2p;
+    if (w.win) {   // a second hierarchy on the same communicator: the window is shared if it is large enough
+        FEMOL_REQUIRE((size_t)halo_doubles <= w.halo_doubles && (size_t)gather_doubles <= w.gather_doubles,
+                      "femol_dist_p2p_open: the communicator's window is open and too small for this hierarchy (use a new communicator)");
+        cudaIpcMemHandle_t h0;
+        FEMOL_CUDA_CHECK(cudaIpcGetMemHandle(&h0, w.win));
+        memcpy(h_handle64, &h0, sizeof(h0));
+        return FEMOL_OK;
+    }
     w.halo_doubles = (size_t)((halo_doubles + 31) & ~31LL);
     w.gather_doubles = (size_t)((gather_doubles + 31) & ~31LL);
     w.off_gather = P2P_OFF_HALO + 4 * w.halo_doubles * 16;
     w.win_bytes = w.off_gather + 2 * w.gather_doubles * 16;
-    FEMOL_CUDA_CHECK(cudaMalloc(&w.win, w.win_bytes));
-    FEMOL_CUDA_CHECK(cudaMemset(w.win, 0, w.win_bytes));
-    FEMOL_CUDA_CHECK(cudaMalloc(&w.ctr, P2P_C_N * sizeof(unsigned long long)));
-    FEMOL_CUDA_CHECK(cudaMemset(w.ctr, 0, P2P_C_N * sizeof(unsigned long long)));
     cudaIpcMemHandle_t h;
-    FEMOL_CUDA_CHECK(cudaIpcGetMemHandle(&h, w.win));
+    if (cudaMalloc(&w.win, w.win_bytes) != cudaSuccess || cudaMemset(w.win, 0, w.win_bytes) != cudaSuccess ||
+        cudaMalloc(&w.ctr, P2P_C_N * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(w.ctr, 0, P2P_C_N * sizeof(unsigned long long)) != cudaSuccess || cudaIpcGetMemHandle(&h, w.win) != cudaSuccess) {
+        femol_set_error("femol_dist_p2p_open: cannot allocate / export the window (%s)", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(w.win); cudaFree(w.ctr);
+        w.win = nullptr; w.ctr = nullptr;
+        cudaGetLastError();
+        return FEMOL_E_CUDA;
+    }
     memcpy(h_handle64, &h, sizeof(h));
     FEMOL_CUDA_CHECK(cudaDeviceSynchronize());
     return FEMOL_OK;
@@ -599,6 +610,7 @@ extern "C" int femol_dist_p2p_open(femol_comm* c, int64_t halo_doubles, int64_t 
 extern "C" int femol_dist_p2p_attach(femol_comm* c, const void* h_handles) {
     FEMOL_REQUIRE(c && h_handles && c->p2p.win, "femol_dist_p2p_attach: open the window first");
     femol_p2p& w = c->p2p;
+    if (w.on) return FEMOL_OK;         // already attached (a shared window)
     for (int r = 0; r < c->nranks; ++r) {
         if (r == c->rank) { w.peers.w[r] = w.win; continue; }
         cudaIpcMemHandle_t h;
@@ -608,6 +620,8 @@ extern "C" int femol_dist_p2p_attach(femol_comm* c, const void* h_handles) {
         if (e != cudaSuccess) {
             femol_set_error("femol_dist_p2p_attach: cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e));
             cudaGetLastError();
+            for (int q = 0; q < r; ++q)       // unmap what was mapped: the transport stays off (NCCL fallback)
+                if (q != c->rank && w.peers.w[q]) { cudaIpcCloseMemHandle(w.peers.w[q]); w.peers.w[q] = nullptr; }
             return FEMOL_E_CUDA;
         }
         w.peers.w[r] = (char*)ptr;
