@@ -280,7 +280,8 @@ int launch_stencil_c(femol_plan_t p, const femol_matrix_free* mf, const double* 
                                           fused ? dot_out : nullptr, red_ws, ep.rhs, ep.dinv, ep.omega));
         femol_count_launch();
     }
-    if (!fused && dot_out) return femol_dot(p->n_nodes * p->ndof, y, dot_with, dot_out, red_ws, st);
+    // (mode 2 fuses y . rhs, the r.z of preconditioned CG; mode 0 fuses y . dot_with)
+    if (!fused && dot_out) return femol_dot(p->n_nodes * p->ndof, y, MODE == 2 ? ep.rhs : dot_with, dot_out, red_ws, st);
     return FEMOL_OK;
 }
 

@@ -617,6 +617,23 @@ class DistributedSIMP_COMP(object):
                                       % (iters.value, relres.value, lp.solver_rtol))
         return self._U
 
+    def solve_static(self, X=None, p=1.0):
+        """K(X^p) U = F on the strip partition - the distributed counterpart of `FEM_Problem.assemble('K', X, p)` +
+        `solve()` (FEM.py:160-214).  X: global densities (array over ALL elements, identical on every rank) or None (solid).
+        Returns (global node ids of the owned rows, their displacements [n_owned_nodes, N_dof]); `solver_info` as usual."""
+        torch = self.torch
+        keep_x, keep_p = self._x, self.p
+        try:
+            if X is None:
+                self._x = torch.ones_like(keep_x)
+            else:
+                self._x = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64)).to(keep_x.device)
+            self.p = p
+            self.solve_displacement()
+        finally:
+            self._x, self.p = keep_x, keep_p
+        return self.owned_displacement()
+
     def iterate(self):
         torch, L = self.torch, self.F_mod._lib
         import torch.distributed as dist

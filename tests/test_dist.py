@@ -410,6 +410,12 @@ def _check_strip_simp(F, fd, kind, nx, ny, n_dist, comm, iters=3):
     nodes, U = opt.owned_displacement()
     U_ref = ref._U.view(-1, 2).cpu().numpy()[nodes]
     assert np.abs(U - U_ref).max() < 1e-6 * np.abs(U_ref).max()
+    # static solve of the solid structure through the same machinery (FEM_Problem.assemble + solve)
+    nodes, U = opt.solve_static()
+    sp = _simp_problem(F, kind, nx, ny)
+    sp.assemble('K')
+    U_ref = sp.solve_device().view(-1, 2).cpu().numpy()[nodes]
+    assert opt.solver_info['converged'] and np.abs(U - U_ref).max() < 1e-6 * np.abs(U_ref).max()
     return opt
 
 

@@ -494,6 +494,31 @@ def test_large_mesh_properties(F):
     assert float(U[torch.from_numpy(fixed).cuda()].abs().max()) == 0.0
 
 
+def test_matrix_free_solve_beyond_one_reduction_grid(F):
+    """4200 x 2100 Q4 plane (17.7 M dof): the matrix-free product needs more CTAs (17 358) than the one-channel grid
+    reduction has slots (8 192), so it runs in chunks and its fused dot products (p . K p in CG, r . z in the last
+    kernel of the V-cycle) become a pass of their own.  A 36 M-dof run found the r . z pass called with a null operand;
+    the solve must converge with the iteration count of the small meshes and satisfy K u = f."""
+    import torch
+    nx, ny = 4200, 2100
+    mesh = F.mesh.rectangle_Q4(float(nx), float(ny), nx, ny)
+    p = F.FEM_Problem('displacement', 'plane', mesh)
+    p.define_materials(F.materials.general_isotropic()); p.define_tensors(1)
+    p.add_fixed_domain(F.domains.inside_box([0], [[0, float(ny)]]))
+    p.add_forces([0, -1.0], F.domains.inside_box([float(nx)], [[ny / 2.0 - 1, ny / 2.0 + 1]]))
+    p.solver_rtol = 1e-8
+    p.assemble('K')
+    U = p.solve_device()
+    info = p.solver_info
+    assert info['preconditioner'] == 'gmg' and info['converged'] and info['iterations'] < 40, info
+    d = p.device
+    y = torch.empty_like(U)
+    F._lib.call('femol_spmv', d.plan, p.K_values.data_ptr(), U.data_ptr(), y.data_ptr(), F._lib.stream())   # assembled CSR operator
+    assert float((y - p._F_dev).norm() / p._F_dev.norm()) < 2e-8
+    del p, U, y
+    torch.cuda.empty_cache()
+
+
 # ---- K6 block kernels (LOBPCG building blocks) vs numpy ---------------------------------------------------------
 def test_block_kernels(F, golden):
     import torch
