@@ -499,3 +499,156 @@ def test_strip_simp_two_gpus(kind, nx, ny, n_dist, transport):
             if p.is_alive():
                 p.kill()
     assert len(results) == len(procs) and all(r[1] == 'ok' for r in results), results
+
+
+# ---- the strip-distributed V-cycle, emulated in numpy over gloo ------------------------------------------------------
+def _strip_vcycle_worker(rank, world, port, kind, nx, ny, n_dist, out_q):
+    """numpy stand-in for csrc/gmg.cu dvcycle + csrc/dist.cu transfers: every rank holds the rows [row0, top] of the
+    operators of the distributed levels, exchanges halo rows over gloo exactly where the device code does (e, t, e_c;
+    NOT before the post-smoothing product), gathers the level-n_dist residual and runs the remaining levels on the
+    whole grid.  After every operation all rows that the device code leaves undefined (everything that is neither
+    owned nor just filled by an exchange) are overwritten with random numbers: the owned rows of the result must still
+    equal the global V-cycle to rounding, i.e. garbage never reaches an owned row."""
+    for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    import femol_oracle as o
+    import cases
+    import numpy_ops
+    from femol_b200 import dist as fd
+    from femol_b200 import mesh as fmesh
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        nd, omega = 2, 0.7
+        gm = {'q4': fmesh.rectangle_Q4, 't6': fmesh.rectangle_T6}[kind](float(nx), float(ny), nx, ny)
+        cells = np.asarray(gm.cells[gm.contains[0]])
+        pts = gm.points[:, :2]
+        hx = np.unique(np.round(pts[:, 0], 9)); hy = np.unique(np.round(pts[:, 1], 9))
+        Nx, Ny = hx.shape[0] - 1, hy.shape[0] - 1
+        li = np.rint(pts[:, 0] / (hx[1] - hx[0])).astype(np.int64); lj = np.rint(pts[:, 1] / (hy[1] - hy[0])).astype(np.int64)
+        node_lat = lj * (Nx + 1) + li
+        lat_node = np.empty(gm.N_nodes, dtype=np.int64); lat_node[node_lat] = np.arange(gm.N_nodes)
+        # global operator in LATTICE order (what every strip uses locally), clamped on the left edge
+        fixed_nodes = np.nonzero(np.isclose(pts[:, 0], 0.0))[0]
+        fixed_idx = (fixed_nodes[:, None] * nd + np.arange(nd)[None]).reshape(-1)
+        arr = {'etype': {'q4': 'Q4', 't6': 'T6'}[kind], 'points': gm.points, 'cells': cells, 'ndof': nd,
+               'tensors': o.iso_tensors(1.0, 0.3, 1.0), 'coat_tensors': None, 'structured': False, 'fixed_idx': fixed_idx}
+        X = cases.density_field(cells.shape[0])
+        K = o.global_matrices(arr, 'K', X, 3).tocsr()
+        dperm = (lat_node[:, None] * nd + np.arange(nd)[None]).reshape(-1)           # lattice dof -> mesh dof
+        K = K[dperm][:, dperm].tocsr()
+        fixed_lat = np.nonzero(np.isin(dperm, fixed_idx))[0]
+        lat = {'Nx': Nx, 'Ny': Ny, 'node_lat': None}
+        rng = np.random.default_rng(3)
+        r = rng.standard_normal(K.shape[0]); r[fixed_lat] = 0.0
+        z_ref, levels, cyc = numpy_ops.numpy_lattice_vcycle(K, lat, fixed_lat, r, omega, nd=nd, return_levels=True)
+        assert len(levels) > n_dist + 1, 'mesh too small for %d distributed levels' % n_dist
+
+        h_up0 = fd.strip_halo_rows(cells, Nx, lat_node, gm.N_nodes)
+        part = fd.StripPartition(Ny, rank, world, n_dist, h_up0=h_up0)
+        garbage = np.random.default_rng(100 + rank)
+        nxs = [Nx]
+        for _ in range(n_dist):
+            nxs.append((nxs[-1] + 1) // 2)
+
+        def dofs(l, row_a, row_b):                       # global (lattice) dofs of the level-l rows [row_a, row_b)
+            npx = nxs[l] + 1
+            return np.arange(row_a * npx * nd, row_b * npx * nd)
+
+        class Strip(object):
+            def __init__(self, l):
+                lev = part.levels[l]
+                self.l, self.lev = l, lev
+                self.rowd = (nxs[l] + 1) * nd
+                self.loc = dofs(l, lev['row0'], lev['top'] + 1)
+                self.lo = (lev['own_begin'] - lev['row0']) * self.rowd          # owned local range [lo, hi)
+                self.hi = (lev['own_end'] - lev['row0']) * self.rowd
+                self.up, self.down = lev['h_up'] * self.rowd, lev['h_down'] * self.rowd
+
+            def poison(self, v, keep_halo):
+                """rows the device leaves undefined: all non-owned rows, except (keep_halo) the exchanged halo rows"""
+                lo_keep = self.lo - (self.up if (keep_halo and rank > 0) else 0)
+                hi_keep = self.hi + (self.down if (keep_halo and rank < world - 1) else 0)
+                v[:lo_keep] = garbage.standard_normal(lo_keep)
+                v[hi_keep:] = garbage.standard_normal(v.shape[0] - hi_keep)
+
+            def exchange(self, v):
+                reqs, bufs = [], {}
+                if rank > 0:
+                    reqs.append(dist.isend(torch.from_numpy(v[self.lo:self.lo + self.down].copy()), rank - 1))
+                    bufs['lo'] = torch.empty(self.up, dtype=torch.float64); reqs.append(dist.irecv(bufs['lo'], rank - 1))
+                if rank < world - 1:
+                    reqs.append(dist.isend(torch.from_numpy(v[self.hi - self.up:self.hi].copy()), rank + 1))
+                    bufs['hi'] = torch.empty(self.down, dtype=torch.float64); reqs.append(dist.irecv(bufs['hi'], rank + 1))
+                for q in reqs:
+                    q.wait()
+                if 'lo' in bufs:
+                    v[self.lo - self.up:self.lo] = bufs['lo'].numpy()
+                if 'hi' in bufs:
+                    v[self.hi:self.hi + self.down] = bufs['hi'].numpy()
+
+        strips = [Strip(l) for l in range(n_dist + 1)]
+
+        def jac(l, rr, e=None):
+            A, D, _ = levels[l]
+            s = strips[l]
+            Aloc = A[s.loc][:, s.loc]
+            res = rr if e is None else rr - Aloc @ e
+            dz = omega * np.einsum('nab,nb->na', D[s.loc[::nd] // nd], res.reshape(-1, nd)).reshape(-1)
+            return dz if e is None else e + dz
+
+        def dvcycle(l, rr):
+            A, D, P = levels[l]
+            s, sc = strips[l], strips[l + 1]
+            Aloc = A[s.loc][:, s.loc]
+            Ploc = P[s.loc][:, sc.loc]
+            e = jac(l, rr)                                  # first sweep
+            s.poison(e, False); s.exchange(e)
+            t = rr - Aloc @ e
+            s.poison(t, False); s.exchange(t)
+            rc = Ploc.T @ t
+            sc.poison(rc, False)
+            if l + 1 < n_dist:
+                ec = dvcycle(l + 1, rc)
+                sc.poison(ec, False); sc.exchange(ec)
+            else:                                           # gather the owned rows, remaining levels on the whole grid
+                pieces = [None] * world
+                dist.all_gather_object(pieces, rc[sc.lo:sc.hi].copy())
+                ec = cyc(l + 1, np.concatenate(pieces))[sc.loc]
+            t = e + Ploc @ ec                                # NO exchange: both inputs are valid on the halo rows
+            s.poison(t, True)
+            out = jac(l, rr, t)
+            s.poison(out, False)
+            return out
+
+        s0 = strips[0]
+        r_loc = r[s0.loc].copy()
+        s0.poison(r_loc, False)
+        z_loc = dvcycle(0, r_loc)
+        err = np.abs(z_loc[s0.lo:s0.hi] - z_ref[s0.loc][s0.lo:s0.hi]).max() / np.abs(z_ref).max()
+        assert err < 1e-12, err
+        out_q.put((rank, 'ok', err))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        out_q.put((rank, 'fail: %s\n%s' % (e, traceback.format_exc()), -1))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,kind,nx,ny,n_dist', [(2, 'q4', 20, 32, 2), (2, 't6', 12, 16, 2), (3, 'q4', 17, 47, 1)])
+def test_strip_vcycle_gloo(world, kind, nx, ny, n_dist):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_strip_vcycle_worker, args=(r, world, port, kind, nx, ny, n_dist, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, it in sorted(results):
+        assert status == 'ok', 'rank %d: %s' % (rank, status)

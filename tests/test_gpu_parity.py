@@ -759,64 +759,7 @@ def test_lattice_vcycle_is_symmetric_positive_and_level1_is_galerkin(F):
     assert rel(Z[0], z_ref) < 1e-6, rel(Z[0], z_ref)
 
 
-def _numpy_lattice_vcycle(K, lat, fixed_dofs, r, omega, nd=2):
-    """V(1,1) cycle with damped block-Jacobi on Galerkin operators; the numpy statement of gmg.cu for a lattice mesh."""
-    import scipy.sparse as sp
-
-    def p1(n):
-        nc = (n + 1) // 2
-        P = np.zeros((n + 1, nc + 1))
-        for i in range(n + 1):
-            if i % 2 == 0: P[i, i // 2] = 1
-            elif i == n: P[i, (i + 1) // 2] = 1
-            else: P[i, i // 2] = .5; P[i, i // 2 + 1] = .5
-        return sp.csr_matrix(P)
-
-    def dinv(A):
-        n = A.shape[0] // nd
-        B = A.tobsr(blocksize=(nd, nd)); B.sort_indices()
-        D = np.zeros((n, nd, nd))
-        for i in range(n):
-            for k in range(B.indptr[i], B.indptr[i + 1]):
-                if B.indices[k] == i: D[i] = B.data[k]
-        return np.linalg.inv(D)
-
-    def jac(A, D, rr, e):
-        res = rr if e is None else rr - A @ e
-        dz = omega * np.einsum('nab,nb->na', D, res.reshape(-1, nd)).reshape(-1)
-        return dz if e is None else e + dz
-
-    levels = []
-    A, Nx, Ny, perm = K, lat['Nx'], lat['Ny'], lat['node_lat']
-    fx = np.zeros(K.shape[0], bool); fx[fixed_dofs] = True
-    while True:
-        if A.shape[0] <= 100 or (Nx == 1 and Ny == 1):
-            levels.append((A, None, None)); break
-        P2 = sp.kron(p1(Ny), p1(Nx)).tocsr()
-        if perm is not None:
-            P2 = P2[perm]
-        P = sp.diags((~fx).astype(float)) @ sp.kron(P2, sp.identity(nd)).tocsr()
-        nxc, nyc = (Nx + 1) // 2, (Ny + 1) // 2
-        I, J = np.meshgrid(np.arange(nxc + 1), np.arange(nyc + 1))
-        fl = (np.minimum(2 * J, Ny) * (Nx + 1) + np.minimum(2 * I, Nx)).reshape(-1)
-        if perm is not None:
-            inv = np.empty_like(perm); inv[perm] = np.arange(perm.shape[0]); fl = inv[fl]
-        fc = fx.reshape(-1, nd)[fl].reshape(-1)
-        keep = sp.diags((~fc).astype(float))
-        P = P @ keep
-        Ac = (P.T @ A @ P + sp.diags(fc.astype(float))).tocsr()
-        levels.append((A, dinv(A), P))
-        A, Nx, Ny, perm, fx = Ac, nxc, nyc, None, fc
-
-    def cyc(l, rr):
-        A, D, P = levels[l]
-        if P is None:
-            # the device inverse decouples dead coarse dofs; none here
-            return np.linalg.solve(A.toarray(), rr)
-        e = jac(A, D, rr, None)
-        e = e + P @ cyc(l + 1, P.T @ (rr - A @ e))
-        return jac(A, D, rr, e)
-    return cyc(0, r)
+from numpy_ops import numpy_lattice_vcycle as _numpy_lattice_vcycle  # noqa: E402
 
 
 def test_gmg_rejects_unstructured(F):
