@@ -82,7 +82,11 @@ def lobpcg(ops, m, k, tol=1e-8, max_iter=500, verbose=False, stall_window=5):
             it -= 1
             break
         lam_prev = lam.copy()
-        ops.precondition()                                      # W <- T R  (fixed dofs zeroed)
+        # soft locking: a pair whose residual already meets the tolerance keeps its (tiny) residual as search
+        # direction instead of an expensive T ~ K^-1 application; it is re-activated if its residual grows again
+        locked = np.zeros(m, dtype=bool)
+        locked[:k] = rel[:k] <= tol
+        ops.precondition(skip=locked)                           # W <- T R  (fixed dofs zeroed)
         # M-orthogonalise W against X, then M-orthonormalise W (Cholesky)
         ops.spmm('M', m, m)
         G = ops.gram('S', 'MS', 0, m, m, m)                     # X' M W
@@ -214,7 +218,7 @@ class DeviceOps(object):
         L.call('femol_block_residual', self.n, self.m, self._p('KS', 0), 3 * self.m, self._p('MS', 0), 3 * self.m,
                L.ptr(self.lam_dev), self._p('S', self.m), 3 * self.m, L.stream())
 
-    def _precondition_gmg(self):
+    def _precondition_gmg(self, skip=None):
         """W <- P K^-1 W column by column (P: zero the masked dofs), K^-1 by a few multigrid-preconditioned CG
         iterations (a variable preconditioner, which LOBPCG tolerates)."""
         import ctypes
@@ -230,6 +234,8 @@ class DeviceOps(object):
                 self._keep = (1 - bits).reshape(-1).to(torch.float64)
         it, rr = ctypes.c_int(0), ctypes.c_double(0.0)
         for c in range(m, 2 * m):
+            if skip is not None and skip[c - m]:
+                continue                                        # locked pair: W = R (already masked: R of a masked X is masked)
             r = S[:, c].contiguous()
             z = torch.zeros_like(r)
             L.call('femol_pcg_gmg', self.plan, self.gmg, L.ptr(self.k_vals), L.ptr(r), L.ptr(z), self.inner_tol,
@@ -238,11 +244,13 @@ class DeviceOps(object):
                 z.mul_(self._keep)
             S[:, c] = z
 
-    def precondition(self):
+    def precondition(self, skip=None):
+        """W <- T W.  skip[c] (optional, per column): leave column c as it is (soft locking of converged pairs; only the
+        column-by-column multigrid path can skip, the block kernels treat all columns together)."""
         L = self._lib
         fixed = L.ptr(self.fixed) if self.fixed is not None else None
         if self.gmg is not None:
-            return self._precondition_gmg()
+            return self._precondition_gmg(skip)
         if self.inner_iters > 0:
             if self._bp_ws is None:
                 nd = int(L.load().femol_block_pcg_workspace_doubles(self.plan, self.m))

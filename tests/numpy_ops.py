@@ -56,7 +56,7 @@ class NumpyOps(object):
         m = self.m
         self._a('S')[:, m:2 * m] = self._a('KS')[:, :m] - self._a('MS')[:, :m] * lam[None, :]
 
-    def precondition(self):
+    def precondition(self, skip=None):
         m = self.m
         W = self.apply_T(self._a('S')[:, m:2 * m])
         W[~self.free] = 0
