@@ -404,6 +404,8 @@ def attach_p2p(F, comm, gmg, world):
     oks = _gather_objects(ok, world)
     torch.cuda.synchronize()
     dist.barrier()
+    if not any(oks):
+        return 'nccl'           # no rank could map its peers (CUDA IPC unavailable): the library keeps using NCCL
     if not all(oks):
         raise L.FemolError('peer-memory transport: some ranks attached and some did not; set FEMOL_DIST_TRANSPORT=nccl')
     return 'p2p'
