@@ -447,8 +447,8 @@ def run_gpu(args):
             roofline = {'kernel': 'stencil_tile_kernel<2,false,32,8,2,2,mode 0|1|2>: matrix-free fine-level K p of PCG and of the V-cycle '
                                   '(launch-weighted over the three epilogue modes)',
                         'bound': 'hbm', 'achieved': tot_b / tot_t / 1e9, 'peak': peak, 'unit': 'GB/s',
-                        'frac': tot_b / tot_t / 1e9 / peak, 'traffic': 54.9e6, 'peak_source': peak_src,
-                        'traffic_source': 'profiles/r01_ncu_stencil_summary.md (mode 0 launch; the vectors are partly L2-resident between kernels)',
+                        'frac': tot_b / tot_t / 1e9 / peak, 'traffic': 55.0e6, 'peak_source': peak_src,
+                        'traffic_source': 'profiles/r02_ncu_summary.md (mode 0 launch: 50.1 MB read + 4.9 MB written; round 1: 54.9 MB; the vectors are partly L2-resident between kernels)',
                         'algorithmic_bytes_per_launch': tot_b / max(1, sum(n_launch)), 'avg_launch_s': tot_t / max(1, sum(n_launch)),
                         'per_mode': [{'mode': m, 'bytes': mf_bytes[m], 'avg_launch_s': mf_t[m], 'GBps': mf_bytes[m] / mf_t[m] / 1e9,
                                       'launches_in_timed_region': n_launch[m]} for m in range(3)],
