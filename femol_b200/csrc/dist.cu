@@ -73,7 +73,8 @@ int load_nccl() {
 // Peer-memory transport (femol_dist_p2p_open / _attach): every rank owns one cudaMalloc'ed WINDOW that all other ranks
 // of the box map through CUDA IPC (NVLink / NVSwitch peer stores).  A window is an array of 16-byte elements, each one
 // double with its own arrival flags (LLElem below):
-//   [P2P_OFF_RED]     red[2 parities][16 ranks][16]                       partial sums of the scalar all-reduce
+//   [P2P_OFF_RED]     red[3 channels][2 parities][16 ranks][16]           partial sums of the scalar all-reduces (channel 0:
+//                     the stand-alone all-reduce kernel; 1 and 2: the reductions fused into the CG kernels, below)
 //   [P2P_OFF_HALO]    halo[2 (from lower, from upper)][2 parities][halo_doubles]
 //   [off_gather]      gather[2 parities][gather_doubles]
 // A transfer = the sender's kernel stores payload + epoch into the receiver's window (slot = epoch parity) with 16-byte
@@ -83,8 +84,10 @@ int load_nccl() {
 // receiver's stream issues after its transfer-k kernel has finished reading slot k.
 constexpr int P2P_MAX_RANKS = 16;
 constexpr int P2P_RED_MAX = 16;
-constexpr size_t P2P_OFF_RED = 0, P2P_OFF_HALO = 2 * P2P_MAX_RANKS * P2P_RED_MAX * 16;
-enum { P2P_C_HALO_EP = 0, P2P_C_RED_EP = 3, P2P_C_GAT_EP = 4, P2P_C_GAT_DONE = 6, P2P_C_ERR = 7, P2P_C_N = 8 };
+constexpr int P2P_RED_CHANNELS = 3;
+constexpr size_t P2P_OFF_RED = 0, P2P_OFF_HALO = (size_t)P2P_RED_CHANNELS * 2 * P2P_MAX_RANKS * P2P_RED_MAX * 16;
+enum { P2P_C_HALO_EP = 0, P2P_C_RED1_EP = 1, P2P_C_RED2_EP = 2, P2P_C_RED_EP = 3, P2P_C_GAT_EP = 4, P2P_C_GAT_DONE = 6, P2P_C_ERR = 7,
+       P2P_C_N = 8 };
 
 struct P2PPeers { char* w[P2P_MAX_RANKS]; };
 
@@ -430,6 +433,35 @@ __device__ __forceinline__ unsigned epoch32(unsigned long long ep) { return (uns
 __device__ __forceinline__ LLElem* win_halo(char* w) { return reinterpret_cast<LLElem*>(w + P2P_OFF_HALO); }
 __device__ __forceinline__ LLElem* win_red(char* w) { return reinterpret_cast<LLElem*>(w + P2P_OFF_RED); }
 
+// ---- dot product + all-reduce in ONE kernel ------------------------------------------------------------------------
+// The CG kernels that produce a partial sum store it straight into every rank's window from their last block (the one
+// that completes the deterministic grid sum), and the kernel that consumes the scalar polls the W contributions and adds
+// them in rank order - no all-reduce kernel in between.  One link = one reduction channel of the windows with its own
+// device epoch counter: producers use epoch counter + 1, the consumer advances the counter once every one of its blocks
+// has read it.  W = 0: not fused (single rank or NCCL transport; the caller runs an all-reduce).
+struct RedLink {
+    P2PPeers peers;
+    unsigned long long* ctr;     // device counters of the communicator
+    int W, me, channel, ctr_idx;
+};
+__device__ __forceinline__ LLElem* red_slot(char* w, int channel, size_t par, int rank, int k) {
+    return win_red(w) + ((((size_t)channel * 2 + par) * P2P_MAX_RANKS + rank) * P2P_RED_MAX + k);
+}
+// one thread: my partial sum k of the link's next epoch -> every rank's window
+__device__ __forceinline__ void red_push(const RedLink& L, int k, double v) {
+    const unsigned long long ep64 = ld_volatile_u64(&L.ctr[L.ctr_idx]) + 1ULL;
+    for (int r = 0; r < L.W; ++r) ll_store(red_slot(L.peers.w[(L.me + r) % L.W], L.channel, (size_t)(ep64 & 1ULL), L.me, k), v, epoch32(ep64));
+}
+// any thread: sum over the ranks (rank order) of partial sum k of the link's next epoch
+__device__ __forceinline__ double red_poll(const RedLink& L, int k) {
+    const unsigned long long ep64 = ld_volatile_u64(&L.ctr[L.ctr_idx]) + 1ULL;
+    double sum = 0.0;
+    for (int r = 0; r < L.W; ++r) sum += ll_wait(red_slot(L.peers.w[L.me], L.channel, (size_t)(ep64 & 1ULL), r, k), epoch32(ep64), L.ctr);
+    return sum;
+}
+// one thread, after EVERY block of the consuming kernel has polled
+__device__ __forceinline__ void red_advance(const RedLink& L) { L.ctr[L.ctr_idx] = ld_volatile_u64(&L.ctr[L.ctr_idx]) + 1ULL; }
+
 // Halo exchange of one vector in ONE CTA (messages are a few lattice rows: 4 - 11 k doubles): store my boundary rows
 // into the neighbours' mailboxes over NVLink, then poll my own mailbox element by element into the ghost rows.  Every
 // microsecond of this kernel is on the critical path of the V-cycle (1 + 3 n_dist exchanges per CG iteration).
@@ -476,8 +508,8 @@ p2p_allreduce_kernel(double* buf, int count, int W, int me, P2PPeers peers, unsi
     const int t = threadIdx.x;
     if (t < W * count) {
         const int peer = t / count, k = t - peer * count;
-        ll_store(win_red(peers.w[peer]) + (par * P2P_MAX_RANKS + me) * P2P_RED_MAX + k, buf[k], ep);
-        s_val[t] = ll_wait(win_red(peers.w[me]) + (par * P2P_MAX_RANKS + peer) * P2P_RED_MAX + k, ep, ctr);   // rank `peer`'s k-th value
+        ll_store(red_slot(peers.w[peer], 0, par, me, k), buf[k], ep);
+        s_val[t] = ll_wait(red_slot(peers.w[me], 0, par, peer, k), ep, ctr);   // rank `peer`'s k-th value
     }
     __syncthreads();
     if (t < count) {
@@ -671,25 +703,37 @@ __global__ void dg_init_finalize(double* sc, double rtol, int restart) {
     sc[G_DONE] = (sc[G_L0] <= rtol * rtol * sc[G_L1]) ? 1.0 : 0.0;
 }
 
-// sc[slot] = a . b over the owned range (local part)
+// out[0] = a . b over the owned range (local part); fused link: the last block also stores it into every rank's window
+// as partial sum k of the link's next epoch
 __global__ void __launch_bounds__(DT)
-dg_dot(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, double* __restrict__ red) {
+dg_dot(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, double* __restrict__ red,
+       const RedLink link, int k) {
     FEMOL_PDL_SYNC();
     __shared__ double s_red[32];
     double acc[1] = {0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc[0] += a[i] * b[i];
-    grid_sum_finish<1>(acc, red, red_ticket(red), out, s_red);
+    if (grid_sum_last<1>(acc, red, red_ticket(red), s_red)) {
+        out[0] = acc[0];
+        if (link.W) red_push(link, k, acc[0]);
+    }
 }
 
 // u += alpha p ; r -= alpha q ; local r.r -> sc[G_L1] ; z = omega Dinv r (the V-cycle's first sweep), owned nodes
 template <int ND>
 __global__ void __launch_bounds__(DT)
 dg_update(int64_t n_nodes, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ u, double* __restrict__ r,
-          double* __restrict__ sc, double* __restrict__ red, const double* __restrict__ dinv, double omega, double* __restrict__ z) {
+          double* __restrict__ sc, double* __restrict__ red, const double* __restrict__ dinv, double omega, double* __restrict__ z,
+          const RedLink pq_link, const RedLink rr_link) {
     FEMOL_PDL_SYNC();
     __shared__ double s_red[32];
+    __shared__ double s_pq;
+    if (pq_link.W) {          // fused all-reduce of p.Kp: every block adds the W contributions itself (rank order)
+        if (threadIdx.x == 0) s_pq = red_poll(pq_link, 0);
+        __syncthreads();
+    }
+    const double pq = pq_link.W ? s_pq : sc[G_PQ];
     const bool done = sc[G_DONE] != 0.0;
-    const double alpha = done ? 0.0 : sc[G_RZN] / sc[G_PQ];
+    const double alpha = done ? 0.0 : sc[G_RZN] / pq;
     double acc[1] = {0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_nodes; i += (int64_t)gridDim.x * blockDim.x) {
         double rv[ND];
@@ -713,12 +757,21 @@ dg_update(int64_t n_nodes, const double* __restrict__ p, const double* __restric
         }
     }
     // every rank takes part in the reduction that follows, converged or not
-    grid_sum_finish<1>(acc, red, red_ticket(red), sc + G_L1, s_red);
+    if (grid_sum_last<1>(acc, red, red_ticket(red), s_red)) {      // the last block: every block has polled p.Kp by now
+        sc[G_L1] = acc[0];
+        if (pq_link.W) { sc[G_PQ] = pq; red_advance(pq_link); }
+        if (rr_link.W) red_push(rr_link, 1, acc[0]);
+    }
 }
 
 // after the all-reduce of (r.z, r.r): rotate the r.z slots, count the iteration, test convergence
-__global__ void dg_iter_finalize(double* sc, int first) {
+__global__ void dg_iter_finalize(double* sc, int first, const RedLink link) {
     FEMOL_PDL_SYNC();
+    if (link.W) {             // fused all-reduce of (r.z, r.r): partial sums 0 (dg_dot) and 1 (dg_update) of the link
+        sc[G_L0] = red_poll(link, 0);
+        if (!first) sc[G_L1] = red_poll(link, 1);
+        red_advance(link);
+    }
     if (sc[G_DONE] != 0.0) return;
     sc[G_RZO] = sc[G_RZN];
     sc[G_RZN] = sc[G_L0];
@@ -787,11 +840,27 @@ int pcg_gmg_dist_run(femol_plan_t plan, femol_gmg* gmg, const double* vals, cons
         true_rel = h_sc[G_FF] > 0.0 ? sqrt(h_sc[G_RR] / h_sc[G_FF]) : 0.0;
         return FEMOL_OK;
     };
+    // reductions fused into the CG kernels when the peer-memory windows are attached (FEMOL_DIST_FUSED_REDUCE=0: separate
+    // all-reduce kernels)
+    RedLink pq_link, rz_link;
+    memset(&pq_link, 0, sizeof(pq_link));
+    memset(&rz_link, 0, sizeof(rz_link));
+    {
+        const char* ef = getenv("FEMOL_DIST_FUSED_REDUCE");
+        if (c->p2p.on && c->nranks > 1 && !(ef && atoi(ef) == 0)) {
+            pq_link.peers = c->p2p.peers; pq_link.ctr = c->p2p.ctr; pq_link.W = c->nranks; pq_link.me = c->rank;
+            rz_link = pq_link;
+            pq_link.channel = 1; pq_link.ctr_idx = P2P_C_RED1_EP;
+            rz_link.channel = 2; rz_link.ctr_idx = P2P_C_RED2_EP;
+        }
+    }
+    const bool fused_red = pq_link.W > 0;
     auto rz_and_direction = [&](int first) -> int {
-        FEMOL_CUDA_CHECK(femol_launch_pdl(dg_dot, dim3(vgrid), dim3(DT), 0, st, n_own, (const double*)(r + off), (const double*)(z + off), sc + G_L0, red));
+        FEMOL_CUDA_CHECK(femol_launch_pdl(dg_dot, dim3(vgrid), dim3(DT), 0, st, n_own, (const double*)(r + off), (const double*)(z + off), sc + G_L0, red, rz_link, 0));
         femol_count_launch();
-        if ((rc = femol_dist_allreduce(c, sc + G_L0, 2, st)) != FEMOL_OK) return rc;
-        FEMOL_CUDA_CHECK(femol_launch_pdl(dg_iter_finalize, dim3(1), dim3(1), 0, st, sc, first));
+        if (fused_red) ++c->p2p.n_red;
+        else if ((rc = femol_dist_allreduce(c, sc + G_L0, 2, st)) != FEMOL_OK) return rc;
+        FEMOL_CUDA_CHECK(femol_launch_pdl(dg_iter_finalize, dim3(1), dim3(1), 0, st, sc, first, rz_link));
         femol_count_launch();
         FEMOL_CUDA_CHECK(femol_launch_pdl(dg_direction, dim3(vgrid), dim3(DT), 0, st, n_own, (const double*)(z + off), p + off, (const double*)sc, first));
         femol_count_launch();
@@ -800,12 +869,13 @@ int pcg_gmg_dist_run(femol_plan_t plan, femol_gmg* gmg, const double* vals, cons
     auto iteration = [&]() -> int {
         if ((rc = femol_dist_exchange(c, p, nd, s, st)) != FEMOL_OK) return rc;
         if ((rc = femol_apply_launch(plan, vals, p, q, nullptr, nullptr, nullptr, st)) != FEMOL_OK) return rc;
-        FEMOL_CUDA_CHECK(femol_launch_pdl(dg_dot, dim3(vgrid), dim3(DT), 0, st, n_own, (const double*)(p + off), (const double*)(q + off), sc + G_PQ, red));
+        FEMOL_CUDA_CHECK(femol_launch_pdl(dg_dot, dim3(vgrid), dim3(DT), 0, st, n_own, (const double*)(p + off), (const double*)(q + off), sc + G_PQ, red, pq_link, 0));
         femol_count_launch();
-        if ((rc = femol_dist_allreduce(c, sc + G_PQ, 1, st)) != FEMOL_OK) return rc;
+        if (fused_red) ++c->p2p.n_red;
+        else if ((rc = femol_dist_allreduce(c, sc + G_PQ, 1, st)) != FEMOL_OK) return rc;
         const double* dv = first_sweep ? dinv0 + s.own_lo * s.row_nodes * nd * nd : nullptr;
-        if (nd == 2) FEMOL_CUDA_CHECK(femol_launch_pdl(dg_update<2>, dim3(ngrid), dim3(DT), 0, st, n_own_nodes, (const double*)(p + off), (const double*)(q + off), u + off, r + off, sc, red, dv, omega0, z + off));
-        else FEMOL_CUDA_CHECK(femol_launch_pdl(dg_update<6>, dim3(ngrid), dim3(DT), 0, st, n_own_nodes, (const double*)(p + off), (const double*)(q + off), u + off, r + off, sc, red, dv, omega0, z + off));
+        if (nd == 2) FEMOL_CUDA_CHECK(femol_launch_pdl(dg_update<2>, dim3(ngrid), dim3(DT), 0, st, n_own_nodes, (const double*)(p + off), (const double*)(q + off), u + off, r + off, sc, red, dv, omega0, z + off, pq_link, rz_link));
+        else FEMOL_CUDA_CHECK(femol_launch_pdl(dg_update<6>, dim3(ngrid), dim3(DT), 0, st, n_own_nodes, (const double*)(p + off), (const double*)(q + off), u + off, r + off, sc, red, dv, omega0, z + off, pq_link, rz_link));
         femol_count_launch();
         if ((rc = femol_gmg_dist_vcycle(gmg, r, z, st, first_sweep)) != FEMOL_OK) return rc;
         return rz_and_direction(0);

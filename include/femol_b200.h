@@ -253,9 +253,10 @@ int femol_dist_allreduce_sum(femol_comm_t comm, double* buf, int64_t count, void
  * (torch.distributed) and every rank attaches them.  From then on a halo exchange is ONE single-CTA kernel per rank: it
  * stores its boundary rows straight into the neighbours' windows over NVLink as 16-byte elements {low word, epoch, high
  * word, epoch} and polls its own window until every element carries the epoch it expects - no fence, no separate flag,
- * one store latency per transfer (NCCL's LL protocol for FP64 payloads).  The 1-2 scalar all-reduces of a CG iteration
- * and the gather of the coarse residual work the same way (all-to-all pushes, summed in rank order: bit-identical on all
- * ranks).  Epochs are device counters, so the launch sequence is static (CUDA-graph capturable).
+ * one store latency per transfer (NCCL's LL protocol for FP64 payloads).  The two scalar all-reduces of a CG iteration
+ * are fused into the CG kernels (the dot-product kernel's last block pushes the local sum to every window, the consuming
+ * kernel polls and adds in rank order: bit-identical on all ranks; FEMOL_DIST_FUSED_REDUCE=0: a separate all-reduce
+ * kernel), and the gather of the coarse residual is an all-to-all push.  Epochs are device counters, so the launch sequence is static (CUDA-graph capturable).
  * femol_dist_p2p_status: 0 healthy, 1 a wait timed out (~2 s: peer lost); h_stats[3] (optional) = halo / all-reduce /
  * gather kernels launched. */
 int femol_gmg_dist_p2p_sizes(femol_gmg_t gmg, int64_t* h_out);
