@@ -767,8 +767,28 @@ class FEM_Problem(object):
         # 105 -> 29; t/h = 100: 15 -> 23 and 35 -> 18; t/h = 4: 177 -> 137 and 147 -> 113 - profiles/r01_plate_hourglass.md)
         return ratio >= 8.0 if free_edge else 8.0 <= ratio <= 50.0
 
+    def _gmg_workspace_views(self, gmg, m):
+        """m workspace views of the current hierarchy (femol_gmg_clone_workspace), created once and kept until the
+        hierarchy is destroyed: LOBPCG solves the m columns of its preconditioner concurrently, one view per column."""
+        if gmg is None or m < 2:
+            return None
+        views = getattr(self, '_gmg_views', None)
+        if views is None:
+            views = self._gmg_views = []
+        try:
+            while len(views) < m:
+                h = ctypes.c_void_p()
+                _lib.call('femol_gmg_clone_workspace', gmg, ctypes.byref(h))
+                views.append(h)
+        except _lib.FemolError:
+            return None                      # no memory for more work vectors: sequential column solves
+        return views[:m]
+
     def _destroy_gmg(self):
         L = _lib.load()
+        for h in getattr(self, '_gmg_views', None) or []:       # the views borrow the hierarchy: they go first
+            L.femol_gmg_destroy(h)
+        self._gmg_views = []
         if getattr(self, '_gmg', None) is not None:
             L.femol_gmg_destroy(self._gmg)
             self._gmg = None
@@ -816,7 +836,7 @@ class FEM_Problem(object):
         gmg = self._gmg_ready() if (self.preconditioner in ('auto', 'gmg') and self._effective_preconditioner() == 'gmg') else None
         ops = _lobpcg.DeviceOps(d.plan, self._Kv, self._Mv, mask, m, _PRECOND[inner], X0,
                                 inner_iters=self.modal_inner_iters, inner_tol=self.modal_inner_tol, gmg=gmg,
-                                gmg_iters=self.modal_gmg_iters)
+                                gmg_iters=self.modal_gmg_iters, gmg_views=self._gmg_workspace_views(gmg, m))
         lam, rel, its = _lobpcg.lobpcg(ops, m, k, tol=self.modal_tol, max_iter=self.modal_max_iter)
         V = ops.vectors()
         self._X_modal = V.clone()

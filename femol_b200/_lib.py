@@ -53,6 +53,7 @@ SIGNATURES = {
     'femol_gmg_create_lattice': (c_int, [c_i64, c_i64, c_int, P, P, P, P, P, P, c_int, c_dbl, P, ctypes.POINTER(c_vp)]),
     'femol_gmg_setup_lattice': (c_int, [P, P, c_int, P, c_int, P, P, P]),
     'femol_gmg_apply': (c_int, [P, P, P, P]),
+    'femol_gmg_clone_workspace': (c_int, [P, ctypes.POINTER(c_vp)]),
     'femol_gmg_attach_modulated': (c_int, [P, P]),
     'femol_plan_create_view': (c_int, [P, ctypes.POINTER(c_vp)]),
     'femol_pcg_gmg_workspace_doubles': (c_i64, [P]),

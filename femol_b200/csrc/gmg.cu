@@ -87,6 +87,7 @@ struct femol_gmg {
     int32_t* child_idx;  // ... ascending (deterministic summation order)
     bool capped;         // femol_gmg_truncate: the last level is a gather level without coarsest-level solve
     GmgDist* dist;       // strip-distributed hierarchy or NULL
+    femol_gmg* parent;   // workspace view (femol_gmg_clone_workspace): operators borrowed from `parent`, own work vectors
 };
 
 namespace {
@@ -1171,6 +1172,10 @@ int femol_gmg_iteration_hint(femol_gmg* g, int set) {
 int femol_gmg_vcycle_internal(femol_gmg* g, const double* r, double* z, cudaStream_t st, double* rz_out, double* red_ws,
                               bool* rz_fused, bool presmoothed) {
     if (rz_fused) *rz_fused = false;
+    if (g->parent) {          // the parent's fine-level operator pointer changes with every set-up
+        g->lv[0].vals = g->parent->lv[0].vals;
+        if (g->mod && g->parent->mod) g->mod->lv[0].vals = g->parent->mod->lv[0].vals;
+    }
     if (g->dist) return femol_gmg_dist_vcycle(g, r, z, st, presmoothed);
     if (g->capped) { femol_set_error("femol_gmg: a truncated hierarchy needs femol_gmg_set_dist"); return FEMOL_E_ARG; }
     if (g->mod) {
@@ -1195,6 +1200,17 @@ int femol_gmg_vcycle_internal(femol_gmg* g, const double* r, double* z, cudaStre
 
 extern "C" int femol_gmg_destroy(femol_gmg* g) {
     if (!g) return FEMOL_OK;
+    if (g->parent) {          // workspace view: only the work vectors (and the view of the attached hierarchy) are its own
+        for (int l = 0; l < g->n_levels; ++l) {
+            Level& L = g->lv[l];
+            if (l > 0) { cudaFree(L.r); cudaFree(L.e); cudaFree(L.r2); cudaFree(L.e2); }
+            cudaFree(L.t);
+        }
+        cudaFree(g->mod_r); cudaFree(g->mod_z);
+        if (g->mod) femol_gmg_destroy(g->mod);
+        delete g;
+        return FEMOL_OK;
+    }
     for (int l = 0; l < g->n_levels; ++l) {
         Level& L = g->lv[l];
         if (l > 0) {
@@ -1480,6 +1496,41 @@ int gmg_setup_impl(femol_gmg* g, const double* e_base, int base_pe, const double
     return FEMOL_OK;
 }
 }  // namespace
+
+// A second set of work vectors on the SAME hierarchy, so that several V-cycles (one per view, each on its own stream)
+// can run concurrently - LOBPCG preconditions its block column by column, and a single multigrid-CG solve is a chain of
+// small latency-bound kernels that leaves most of the GPU idle.  The view borrows every operator of `g` (plans, values,
+// block inverses, masks, the coarsest inverse) and must be destroyed before it; it follows later femol_gmg_setup calls of
+// `g` automatically.  Not for distributed hierarchies.
+extern "C" int femol_gmg_clone_workspace(femol_gmg* g, femol_gmg** out) {
+    FEMOL_REQUIRE(g && out, "femol_gmg_clone_workspace: null argument");
+    FEMOL_REQUIRE(!g->dist && !g->capped && !g->parent, "femol_gmg_clone_workspace: plain hierarchies only");
+    femol_gmg* v = new femol_gmg(*g);
+    v->parent = g;
+    v->mod = nullptr; v->mod_r = nullptr; v->mod_z = nullptr;
+    v->fused_from = v->cluster_from = v->solo_from = v->n_levels;      // those kernels use the parent's descriptors
+    v->hint_iters = g->hint_iters;
+    for (int l = 0; l < v->n_levels; ++l) { Level& L = v->lv[l]; L.r = L.e = L.r2 = L.e2 = L.t = nullptr; }
+    bool ok = true;
+    for (int l = 0; l < v->n_levels && ok; ++l) {
+        Level& L = v->lv[l];
+        ok = cudaMalloc(&L.t, L.n * sizeof(double)) == cudaSuccess;
+        if (l > 0) ok = ok && cudaMalloc(&L.r, L.n * sizeof(double)) == cudaSuccess && cudaMalloc(&L.e, L.n * sizeof(double)) == cudaSuccess &&
+                         cudaMalloc(&L.r2, L.n * sizeof(double)) == cudaSuccess && cudaMalloc(&L.e2, L.n * sizeof(double)) == cudaSuccess;
+    }
+    if (ok && g->mod) {
+        ok = femol_gmg_clone_workspace(g->mod, &v->mod) == FEMOL_OK &&
+             cudaMalloc(&v->mod_r, g->lv[0].n * sizeof(double)) == cudaSuccess && cudaMalloc(&v->mod_z, g->lv[0].n * sizeof(double)) == cudaSuccess;
+    }
+    if (!ok) {
+        femol_gmg_destroy(v);
+        cudaGetLastError();
+        femol_set_error("femol_gmg_clone_workspace: out of device memory");
+        return FEMOL_E_CUDA;
+    }
+    *out = v;
+    return FEMOL_OK;
+}
 
 extern "C" int femol_gmg_info(femol_gmg* g, int64_t* h_info /* [0]=levels, then (nx, ny) per level */) {
     FEMOL_REQUIRE(g && h_info, "femol_gmg_info: null argument");

@@ -128,11 +128,13 @@ class DeviceOps(object):
     """CUDA implementation of the block operations (csrc/lobpcg.cu through the C-ABI)."""
 
     def __init__(self, plan, k_vals, m_vals, fixed_mask, m, precond_kind, X0, inner_iters=0, inner_tol=1e-2, gmg=None,
-                 gmg_iters=8):
+                 gmg_iters=8, gmg_views=None):
         """precond_kind: diagonal / block-diagonal inverse used directly (inner_iters = 0) or as the inner
         preconditioner of `inner_iters` block-CG iterations on K (T ~ K^-1, femol_block_pcg).
         gmg: multigrid hierarchy of K (femol_gmg handle, structured grids): T ~ K^-1 by at most `gmg_iters`
-        multigrid-preconditioned CG iterations per column (femol_pcg_gmg) instead of the block-CG."""
+        multigrid-preconditioned CG iterations per column (femol_pcg_gmg) instead of the block-CG.
+        gmg_views: m workspace views of `gmg` (femol_gmg_clone_workspace, owned by the caller): the columns are then
+        solved concurrently, one stream and one host thread per column."""
         import torch
         from . import _lib
         self._lib, self._torch = _lib, torch
@@ -140,9 +142,11 @@ class DeviceOps(object):
         self.m = m
         self.inner_iters, self.inner_tol = int(inner_iters), float(inner_tol)
         self.gmg, self.gmg_iters = gmg, int(gmg_iters)
+        self._given_views = list(gmg_views) if gmg_views else []
         self._bp_ws = None
         self._gmg_ws = None
         self._keep = None
+        self._views, self._streams, self._pool = [], [], None
         n = X0.shape[0]
         self.n = n
         dev = X0.device
@@ -218,31 +222,79 @@ class DeviceOps(object):
         L.call('femol_block_residual', self.n, self.m, self._p('KS', 0), 3 * self.m, self._p('MS', 0), 3 * self.m,
                L.ptr(self.lam_dev), self._p('S', self.m), 3 * self.m, L.stream())
 
-    def _precondition_gmg(self, skip=None):
-        """W <- P K^-1 W column by column (P: zero the masked dofs), K^-1 by a few multigrid-preconditioned CG
-        iterations (a variable preconditioner, which LOBPCG tolerates)."""
+    def _gmg_setup_concurrent(self):
+        """One workspace view of the hierarchy (given by the caller), one stream, one PCG workspace and one host thread
+        per column: a single multigrid-CG solve is a chain of small latency-bound kernels, m of them side by side fill
+        the GPU.  FEMOL_MODAL_CONCURRENT=0 (or no views): one column after the other on the current stream."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        L, torch = self._lib, self._torch
+        dev = self.buf[0]['S'].device
+        nd = int(L.load().femol_pcg_gmg_workspace_doubles(self.plan))
+        self._gmg_ws = [torch.empty(nd, dtype=torch.float64, device=dev)]
+        if self.fixed is not None:
+            ndof = self.n // self._n_nodes()
+            bits = (self.fixed.to(torch.int32)[:, None] >> torch.arange(ndof, device=dev, dtype=torch.int32)[None]) & 1
+            self._keep = (1 - bits).reshape(-1).to(torch.float64)
+        self._views, self._streams, self._pool = [], [], None
+        if os.environ.get('FEMOL_MODAL_CONCURRENT', '1') != '0' and self.m > 1 and len(self._given_views) >= self.m:
+            self._views = self._given_views[:self.m]
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.m)]
+            self._gmg_ws = [torch.empty(nd, dtype=torch.float64, device=dev) for _ in range(self.m)]
+            self._pool = ThreadPoolExecutor(max_workers=self.m)
+
+    def __del__(self):
+        try:
+            if self._pool is not None:
+                self._pool.shutdown(wait=True)
+        except Exception:
+            pass
+
+    def _solve_column(self, c, gmg, ws, stream):
+        """z = (approximately) K^-1 S[:, c] by at most gmg_iters multigrid-CG iterations, written back to S[:, c]."""
         import ctypes
         L, torch = self._lib, self._torch
-        m = self.m
         S = self.buf[self.cur]['S']
-        if self._gmg_ws is None:
-            nd = int(L.load().femol_pcg_gmg_workspace_doubles(self.plan))
-            self._gmg_ws = torch.empty(nd, dtype=torch.float64, device=S.device)
-            if self.fixed is not None:
-                ndof = self.n // self._n_nodes()
-                bits = (self.fixed.to(torch.int32)[:, None] >> torch.arange(ndof, device=S.device, dtype=torch.int32)[None]) & 1
-                self._keep = (1 - bits).reshape(-1).to(torch.float64)
         it, rr = ctypes.c_int(0), ctypes.c_double(0.0)
-        for c in range(m, 2 * m):
-            if skip is not None and skip[c - m]:
-                continue                                        # locked pair: W = R (already masked: R of a masked X is masked)
-            r = S[:, c].contiguous()
-            z = torch.zeros_like(r)
-            L.call('femol_pcg_gmg', self.plan, self.gmg, L.ptr(self.k_vals), L.ptr(r), L.ptr(z), self.inner_tol,
-                   self.gmg_iters, L.ptr(self._gmg_ws), ctypes.byref(it), ctypes.byref(rr), L.stream())
-            if self._keep is not None:
-                z.mul_(self._keep)
-            S[:, c] = z
+        r = S[:, c].contiguous()
+        z = torch.zeros_like(r)
+        L.call('femol_pcg_gmg', self.plan, gmg, L.ptr(self.k_vals), L.ptr(r), L.ptr(z), self.inner_tol, self.gmg_iters, L.ptr(ws),
+               ctypes.byref(it), ctypes.byref(rr), stream)
+        if self._keep is not None:
+            z.mul_(self._keep)
+        S[:, c] = z
+
+    def _precondition_gmg(self, skip=None):
+        """W <- P K^-1 W column by column (P: zero the masked dofs), K^-1 by a few multigrid-preconditioned CG
+        iterations (a variable preconditioner, which LOBPCG tolerates); the columns are solved concurrently, each on its
+        own stream with its own workspace view of the hierarchy."""
+        L, torch = self._lib, self._torch
+        m = self.m
+        if self._gmg_ws is None:
+            self._gmg_setup_concurrent()
+        cols = [c for c in range(m, 2 * m) if not (skip is not None and skip[c - m])]   # locked pairs keep W = R
+        if not self._views:
+            for c in cols:
+                self._solve_column(c, self.gmg, self._gmg_ws[0], L.stream())
+            return
+        main = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(main)
+        dev_index = self.buf[0]['S'].device.index
+
+        def work(c):
+            k = c - m
+            torch.cuda.set_device(dev_index)
+            s = self._streams[k]
+            s.wait_event(start)
+            with torch.cuda.stream(s):
+                self._solve_column(c, self._views[k], self._gmg_ws[k], s.cuda_stream)
+                done = torch.cuda.Event()
+                done.record(s)
+            return done
+
+        for done in list(self._pool.map(work, cols)):
+            main.wait_event(done)
 
     def precondition(self, skip=None):
         """W <- T W.  skip[c] (optional, per column): leave column c as it is (soft locking of converged pairs; only the

@@ -195,6 +195,11 @@ int femol_gmg_setup_lattice(femol_gmg_t gmg, const double* e_base, int base_pe, 
  * NULL detaches; the caller owns `mod`. */
 int femol_gmg_attach_modulated(femol_gmg_t gmg, femol_gmg_t mod);
 
+/* A second set of work vectors on the same hierarchy: V-cycles / femol_pcg_gmg solves on different views (each on its own
+ * stream, from its own host thread) run concurrently.  A view borrows every operator of `gmg`, follows its later set-ups
+ * and must be destroyed (femol_gmg_destroy) before it.  Used by LOBPCG, which preconditions its block column by column. */
+int femol_gmg_clone_workspace(femol_gmg_t gmg, femol_gmg_t* out);
+
 /* [0] = levels, then (nx, ny) per level */
 int femol_gmg_apply(femol_gmg_t gmg, const double* r, double* z, void* stream); /* z = V-cycle(r) */
 int64_t femol_pcg_gmg_workspace_doubles(femol_plan_t plan);
