@@ -1161,3 +1161,50 @@ def test_single_precision_products(F, kind, nx, ny):
         assert rel(y.cpu().numpy(), refs[mode]) < 1e-13, mode
     with pytest.raises(L.FemolError):
         L.call('femol_apply_f32', d.plan, v32.data_ptr(), xd.data_ptr(), xd.data_ptr(), 0, None, None, 0.0, L.stream())
+
+
+@pytest.mark.parametrize('model', ['plane', 'plate'])
+def test_gmg_workspace_views(F, model):
+    """femol_gmg_clone_workspace: a view applies the same V-cycle as its hierarchy (bit for bit: same kernels, same
+    operators), follows a later set-up for new densities, and two views on two streams run concurrently without
+    disturbing each other (LOBPCG solves the columns of its preconditioner this way)."""
+    import torch
+    p, x = _gmg_problem(F, 41, 23, model)
+    p.assemble('K', X={'quad': x}, p=3)
+    g = p._gmg_ready()
+    L = F._lib
+    d = p.device
+    views = []
+    for _ in range(2):
+        h = ctypes.c_void_p()
+        L.call('femol_gmg_clone_workspace', g, ctypes.byref(h))
+        views.append(h)
+    try:
+        rng = np.random.default_rng(2)
+        R = [torch.from_numpy(rng.standard_normal(d.n)).cuda() for _ in range(2)]
+
+        def apply(h, r, stream=None):
+            z = torch.empty_like(r)
+            L.call('femol_gmg_apply', h, r.data_ptr(), z.data_ptr(), stream if stream is not None else L.stream())
+            return z
+
+        for round_ in range(2):
+            ref = [apply(g, r) for r in R]
+            torch.cuda.synchronize()
+            streams = [torch.cuda.Stream() for _ in views]
+            out = []
+            for h, r, s in zip(views, R, streams):
+                with torch.cuda.stream(s):
+                    out.append(apply(h, r, s.cuda_stream))
+            torch.cuda.synchronize()
+            for a, b in zip(ref, out):
+                assert torch.equal(a, b)
+            # new densities: the hierarchy is refreshed, the views follow
+            x2 = cases.density_field(p.mesh.N_ele, seed=9 + round_)
+            p.assemble('K', X={'quad': x2}, p=3)
+            p._gmg_ready()
+        with pytest.raises(L.FemolError):
+            L.call('femol_gmg_clone_workspace', views[0], ctypes.byref(ctypes.c_void_p()))    # no views of views
+    finally:
+        for h in views:
+            L.load().femol_gmg_destroy(h)
