@@ -290,3 +290,42 @@ def test_tracked_force_vector_flags_in_place_edits():
     assert F.dirty and F[5] == 2.0
     G = np.array(F, dtype=np.float64)                              # private copies are plain arrays
     assert type(G) is np.ndarray
+
+
+def test_unique_rows_equals_numpy_unique():
+    """mesh._unique_rows (T3 -> T6 mid-side nodes, mesh.py:485-520 of the reference uses np.unique(axis=0)): same unique
+    rows, same inverse, on lattice mid-points and on random rows with many duplicates; empty-free edge cases."""
+    from femol_b200 import mesh as fmesh
+    rng = np.random.default_rng(0)
+    for a in (np.round(rng.random((5000, 3)) * 12) / 4, rng.standard_normal((300, 3)), np.zeros((7, 3)), np.array([[1.0, 2.0, 0.0]])):
+        u0, i0 = np.unique(a, axis=0, return_inverse=True)
+        u1, i1 = fmesh._unique_rows(a)
+        assert np.array_equal(u0, u1) and np.array_equal(np.asarray(i0).reshape(-1), i1)
+    m = fmesh.rectangle_T6(3.0, 2.0, 6, 4)
+    assert m.N_nodes == (2 * 6 + 1) * (2 * 4 + 1) and m.cells['triangle'].shape == (48, 6)
+    # node and cell numbering of the T6 mesh = the oracle's restatement of Mesh.make_triangles_quad (pinned to the reference)
+    import femol_oracle as o
+    pts, tri = o.rectangle_points_tris(3.0, 2.0, 6, 4)
+    pts6, tri6 = o.t3_to_t6(pts, tri)
+    assert np.array_equal(np.asarray(m.cells['triangle']), tri6) and np.allclose(m.points[:, :2], np.asarray(pts6)[:, :2], rtol=0, atol=0)
+
+
+def test_filter_neighbour_list_equals_sparse_distance_matrix():
+    """TOM_SIMP.neighbour_distances (neighbour list of the mesh-independency filter on unstructured meshes,
+    TOM_SIMP.py:237-267) against the direct statement `sparse_distance_matrix` minus its zeros: same pattern, same
+    distances - including an empty list and two coincident centres (a zero distance off the diagonal is dropped)."""
+    from scipy.spatial import cKDTree
+    import femol_b200 as F
+    from femol_b200 import TOM_SIMP
+    rng = np.random.default_rng(1)
+    for mesh in (F.mesh.rectangle_T6(7., 5., 7, 5), F.mesh.rectangle_T3(9., 4., 9, 4)):
+        mesh.compute_element_centers()
+        c = mesh.all_cell_centers + 0.05 * rng.standard_normal(mesh.all_cell_centers.shape)
+        c[3] = c[2]
+        for r in (0.05, 0.8, 1.5, 2.7):
+            tree = cKDTree(c)
+            D = tree.sparse_distance_matrix(tree, r, output_type='coo_matrix').tocsr()
+            D.setdiag(0); D.eliminate_zeros(); D.sort_indices()
+            E = TOM_SIMP.neighbour_distances(c, r)
+            assert D.shape == E.shape and np.array_equal(D.indptr, E.indptr) and np.array_equal(D.indices, E.indices)
+            assert D.nnz == 0 or np.abs(D.data - E.data).max() < 1e-15
