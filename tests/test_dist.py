@@ -652,3 +652,35 @@ def test_strip_vcycle_gloo(world, kind, nx, ny, n_dist):
         p.join(timeout=60)
     for rank, status, it in sorted(results):
         assert status == 'ok', 'rank %d: %s' % (rank, status)
+
+
+def test_strip_partition_invariants_property():
+    """Random (rows, ranks, levels): whenever a partition exists its levels tile the rows, every strip coarsens like the
+    global grid, and pick_levels never proposes strips thinner than four alignment units."""
+    from hypothesis import given, settings, strategies as st
+    from femol_b200.dist import StripPartition
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(8, 6000), st.integers(1, 8), st.integers(1, 6), st.integers(1, 2))
+    def check(Ny, world, n_dist, h_up0):
+        try:
+            parts = [StripPartition(Ny, r, world, n_dist, h_up0=h_up0) for r in range(world)]
+        except ValueError:
+            return                                        # strips too thin for this many levels: rejected, fine
+        A = 1 << n_dist
+        assert all(c % A == 0 for c in parts[0].cuts[1:-1])
+        ny_g = Ny
+        for l in range(n_dist + 1):
+            assert [p.levels[l]['own_begin'] for p in parts][1:] == [p.levels[l]['own_end'] for p in parts][:-1]
+            assert parts[0].levels[l]['own_begin'] == 0 and parts[-1].levels[l]['own_end'] == ny_g + 1
+            for p in parts:
+                lev = p.levels[l]
+                assert lev['row0'] <= lev['own_begin'] < lev['own_end'] <= lev['top'] + 1 <= ny_g + 1
+                if l < n_dist:
+                    nxt = p.levels[l + 1]
+                    assert lev['row0'] % 2 == 0 and lev['row0'] // 2 == nxt['row0']
+                    assert (lev['top'] - lev['row0'] + 1) // 2 == nxt['top'] - nxt['row0']
+            ny_g = (ny_g + 1) // 2
+        n = StripPartition.pick_levels(2 * Ny, Ny, world)
+        assert n == 1 or (Ny + 1) // world >= 4 * (1 << n)
+    check()
